@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py - audio samples/s of the TCN/GCN forward on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm (oracle port of the reference forward)
+
+A "step" is one forward of the workload: BASELINE.json configs[1] (cfg2: TCN 10 blocks,
+32 ch, k = 15, dilations 2**i, one 10 s clip @ 48 kHz mono) per GPU; with --gpus N every
+rank runs its own shard of clips (weak scaling, no data-path collective; NCCL only
+broadcasts the weight blob once).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+SR = 48000
+WORKLOADS = {
+    # name: (arch, ctor kwargs, seconds)
+    "cfg2": ("TCN", dict(n_channels=32, n_layers=10, dilation_growth=2, kernel_size=15, cond_dim=2), 10.0),
+    "cfg3": ("GCN", dict(n_blocks=10, n_channels=32, dilation_growth=2, kernel_size=15, cond_dim=2), 10.0),
+    "cfg1": ("TCN", dict(n_channels=16, n_layers=4, dilation_growth=2, kernel_size=3, cond_dim=2), 1.0),
+}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]), bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def randomise_state(model, seed=0):
+    """Default torch init under manual_seed(seed) happened at construction; give BatchNorm
+    non-trivial running stats and PReLU slopes so the fold is exercised."""
+    g1 = torch.Generator().manual_seed(1)
+    g2 = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for blk in model.blocks:
+            if hasattr(blk, "film"):
+                blk.film.bn.running_mean.copy_(torch.randn(blk.film.bn.running_mean.shape, generator=g1) * 0.5)
+                blk.film.bn.running_var.copy_(0.2 + 1.8 * torch.rand(blk.film.bn.running_var.shape, generator=g1))
+            if hasattr(blk, "act"):
+                blk.act.weight.copy_(0.05 + 0.85 * torch.rand(blk.act.weight.shape, generator=g2))
+
+
+def build_model(workload):
+    import neural_audio_spring_reverb_b200 as N
+    arch, kw, seconds = WORKLOADS[workload]
+    torch.manual_seed(0)
+    if arch == "TCN":
+        m = N.TCN(**kw)
+    else:
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = N.GCN(**kw)
+    randomise_state(m)
+    return m.eval(), arch, kw, int(seconds * SR)
+
+
+def per_sample_costs(arch, kw):
+    """Algorithmic bytes and FLOPs per output sample: per fused block
+    4*(Cin+Cout) bytes and 2*Cin*W*k + 2*Cin*Cout FLOPs; last block fused with out_net."""
+    C, k = kw["n_channels"], kw["kernel_size"]
+    n = kw.get("n_layers", kw.get("n_blocks"))
+    W = 2 * C if arch == "GCN" else C
+    rows = []
+    for i in range(n):
+        cin = 1 if i == 0 else C
+        cout_bytes = 1 if i == n - 1 else C
+        flops = 2 * cin * W * k + 2 * cin * C + (2 * C if i == n - 1 else 0)
+        rows.append(dict(bytes=4 * (cin + cout_bytes), flops=flops))
+    return rows
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_reference_arm(args):
+    """The reference's CPU forward (oracle port on the same ATen CPU operators), all host threads."""
+    from oracle import nasr_oracle as O
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model, arch, kw, T = build_model(args.workload)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # bounded sample: one clip, length chosen so K + W forwards finish in a few minutes
+    Ts = min(T, int(args.cpu_seconds * SR))
+    x = O.make_input(1, 1, Ts)
+    cond = torch.full((1, kw["cond_dim"]), 0.5)
+    for _ in range(max(1, min(args.warmup, 1))):
+        O.forward(sd, model.dilations, x, cond)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        O.forward(sd, model.dilations, x, cond)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    value = Ts / best
+    line = dict(impl="reference", metric="audio samples/sec (48 kHz mono)", value=value, unit="samples/s",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * statistics.mean(times),
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=args.workload, arch=arch, **kw, clip_seconds=Ts / SR, clips=1,
+                            note="reference forward restated on ATen CPU ops (oracle port); one clip, best of K"),
+                cpu_baseline=dict(value=value, unit="samples/s", cores=cores, kind="port",
+                                  sample=f"1 clip x {Ts / SR:.1f} s, fp32, {cores} threads, best of {args.steps}"),
+                e2e=dict(value=value, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--clips-per-gpu", type=int, default=1)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="clip length of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+
+    if args.impl == "reference":
+        return cpu_reference_arm(args)
+
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from neural_audio_spring_reverb_b200.build import build_native
+    if rank == 0:
+        build_native()
+    if world > 1:
+        dist.barrier()
+
+    model, arch, kw, T = build_model(args.workload)
+    # one-time weight broadcast over NCCL: every rank ends up with rank 0's blob
+    if world > 1:
+        blob = model.weight_blob().to(dev)
+        if rank != 0:
+            blob.zero_()
+        dist.broadcast(blob, src=0)
+        model.load_weight_blob(blob.cpu())
+    model = model.to(dev).eval()
+    eng = model._engine()
+
+    B = args.clips_per_gpu
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    x = torch.rand((B, 1, T), device=dev, generator=g) * 2 - 1
+    cond = torch.full((B, kw["cond_dim"]), 0.5, device=dev)
+    x_host = x.cpu().pin_memory()
+    cond_host = cond.cpu().pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing (value) ----
+    for _ in range(args.warmup):
+        y = model(x, cond)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s, e in ev:
+        flush.zero_()                      # L2 flush between timed iterations
+        s.record()
+        y = model(x, cond)
+        e.record()
+    barrier()
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [s.elapsed_time(e) for s, e in ev]
+    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms) / 1e3
+    value = world * B * T * args.steps / total_s
+
+    # ---- end to end through the public API with host buffers ----
+    for _ in range(3):
+        model(x_host, cond_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        y_host = model(x_host, cond_host)
+    torch.cuda.synchronize(dev)
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * T * args.steps / float(e2e_s)
+
+    # ---- live per-kernel timing for the roofline (rank 0) ----
+    line = None
+    if rank == 0:
+        yb = torch.empty_like(y)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        eng.set_cond(cond.data_ptr(), B, stream)
+        acc = None
+        reps = 5
+        for _ in range(reps):
+            flush.zero_()
+            ms = eng.forward_profiled(x.data_ptr(), yb.data_ptr(), B, T, stream)
+            acc = ms if acc is None else [a + b for a, b in zip(acc, ms)]
+        block_ms = [a / reps for a in acc]
+        costs = per_sample_costs(arch, kw)
+        pk = peaks()
+        n = len(block_ms)
+        paths = [eng.block_path(i) for i in range(n)]
+        # dominant kernel = the mid-network block kernel (blocks 1..n-1 share it); report its average launch
+        mid = list(range(1, n)) if n > 1 else [0]
+        dom_ms = sum(block_ms[i] for i in mid) / len(mid)
+        dom_bytes = sum(costs[i]["bytes"] for i in mid) / len(mid) * B * T
+        dom_flops = sum(costs[i]["flops"] for i in mid) / len(mid) * B * T
+        gbs = dom_bytes / (dom_ms * 1e-3) / 1e9
+        tfs = dom_flops / (dom_ms * 1e-3) / 1e12
+        tensor_path = all(paths[i] == 1 for i in mid)
+        hbm_frac = gbs / pk["hbm"]
+        tensor_frac = tfs / pk["bf16"]
+        if tensor_path and tensor_frac >= hbm_frac:
+            roof = dict(bound="tensor", achieved=tfs, peak=pk["bf16"], unit="TFLOP/s", frac=tensor_frac, traffic=None)
+        else:
+            roof = dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=hbm_frac, traffic=None)
+        roof.update(kernel="tc_block_kernel" if tensor_path else "generic_block_kernel (fp32 FFMA)",
+                    peak_source=pk["source"], launch_ms=dom_ms, hbm_gbs=gbs, hbm_frac=hbm_frac,
+                    useful_tflops=tfs, bf16_peak_frac=tensor_frac, fp32_ffma_frac_of_75tf=tfs / 75.0,
+                    block_ms=block_ms, block_paths=paths,
+                    whole_net_hbm_gbs=sum(c["bytes"] for c in costs) * B * T / (sum(block_ms) * 1e-3) / 1e9)
+        tpath = ROOT / "profiles" / "traffic.json"
+        if tpath.exists():
+            try:
+                roof["traffic"] = json.loads(tpath.read_text()).get(roof["kernel"].split(" ")[0])
+            except Exception:
+                pass
+
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle import nasr_oracle as O
+            cores = os.cpu_count() or 1
+            Ts = min(T, int(args.cpu_seconds * SR))
+            sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+            xs = x_host[:1, :, :Ts].clone()
+            cs = cond_host[:1].clone()
+            secs = O.time_forward(sd, model.dilations, xs, cs, repeats=3, threads=cores)
+            # the CPU forward doubles as a full-size parity check of this run
+            ref = O.forward(sd, model.dilations, xs, cs)
+            got = model(x[:1, :, :Ts], cond[:1]).cpu()
+            perr = float((got - ref).abs().max() / ref.abs().max())
+            cpu = dict(value=Ts / secs, unit="samples/s", cores=cores, kind="port",
+                       sample=f"1 clip x {Ts / SR:.1f} s of the same workload, fp32, {cores} threads, best of 3",
+                       parity_rel_err_vs_gpu=perr)
+
+        line = dict(metric="audio samples/sec (48 kHz mono)", value=value, unit="samples/s", n_gpus=world,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=total_s * 1e3 / args.steps,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=args.workload, arch=arch, **kw, clip_seconds=T / SR, clips_per_gpu=B,
+                                global_clips=world * B, sample_rate=SR, l2="flushed between timed iterations (256 MiB write)",
+                                parallelism=f"clips sharded over {world} GPU(s), NCCL weight broadcast only"),
+                    e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=int(x_host.numel() * 4 + cond_host.numel() * 4),
+                             d2h_bytes_per_step=int(y_host.numel() * 4)),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,165 @@
+/*
+ * nasr_b200.h — C ABI of libnasr_b200.so, the B200 (sm_100a) engine for the
+ * TCN / GCN eval-mode forward of francescopapaleo/neural-audio-spring-reverb.
+ *
+ * The reference has no FFI of its own (pure Python / PyTorch); the drop-in
+ * boundary is its Python surface.  Every entry point below names the
+ * reference interface it replaces (paths relative to the reference root,
+ * src/nasr = src/neural_audio_spring_reverb):
+ *
+ *   nasr_engine_create     <- TCN.__init__ / GCN.__init__ + load_state_dict
+ *                             (src/nasr/networks/tcn.py:94-148, gcn.py:80-138,
+ *                              networks/model_utils.py:160-163)
+ *   nasr_set_cond          <- FiLM.forward's adaptor Linear + eval BatchNorm
+ *                             (src/nasr/networks/custom_layers.py:32-42)
+ *   nasr_forward           <- TCN.forward / GCN.forward
+ *                             (src/nasr/networks/tcn.py:150-155, gcn.py:140-147)
+ *   nasr_forward_host      <- the timed region of make_inference: host tensor
+ *                             -> device -> model(input, c) -> host
+ *                             (src/nasr/inference.py:36-61,77)
+ *   nasr_stream_reset /
+ *   nasr_forward_chunk     <- PaddingCached / Conv1dCached streaming state
+ *                             (src/nasr/wrapper.py:14-57)
+ *   nasr_block_forward     <- TCNBlock.forward / GCNBlock.forward on its own
+ *                             (src/nasr/networks/tcn.py:73-86, gcn.py:53-61)
+ *
+ * Conventions
+ *   - All tensors are fp32, contiguous, reference layout: x [B, in_ch, T],
+ *     y [B, out_ch, T], cond [B, cond_dim].
+ *   - Pointers named *_dev are device pointers on the engine's device; *_host
+ *     are host pointers (pinned memory makes the copies asynchronous).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     All device work is enqueued on it; nothing synchronises internally
+ *     except nasr_forward_host, which returns after y_host is complete.
+ *   - Every function returns NASR_OK (0) or a negative nasr_status; the text
+ *     of the last error on a handle is available from nasr_last_error().
+ *     No C++ exception crosses this boundary.
+ *   - A handle is bound to one device and is not thread-safe.
+ *   - There is no CPU fallback: without a CUDA device nasr_engine_create
+ *     fails with NASR_ERR_CUDA.
+ */
+#ifndef NASR_B200_H
+#define NASR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NASR_API __attribute__((visibility("default")))
+#else
+#define NASR_API
+#endif
+
+#define NASR_MAX_BLOCKS 64
+
+typedef enum nasr_status {
+  NASR_OK = 0,
+  NASR_ERR_INVALID = -1,     /* bad argument / unsupported shape (Python: ValueError)   */
+  NASR_ERR_CUDA = -2,        /* CUDA runtime / driver failure     (Python: RuntimeError) */
+  NASR_ERR_STATE = -3,       /* call order: cond not set, stream not reset, ...          */
+  NASR_ERR_NOMEM = -4        /* device or host allocation failed                         */
+} nasr_status;
+
+enum { NASR_ARCH_TCN = 0, NASR_ARCH_GCN = 1 };
+
+/* precision / kernel selection */
+enum {
+  NASR_PATH_AUTO = 0,        /* tensor-core (tcgen05 split-16) blocks where eligible, else fp32 FFMA */
+  NASR_PATH_FP32 = 1         /* fp32 FFMA kernels only                                              */
+};
+
+/*
+ * Model descriptor = the constructor arguments of the reference classes.
+ *   TCN(n_channels, n_layers, dilation_growth, in_ch, out_ch, kernel_size, cond_dim)
+ *   GCN(in_ch, out_ch, n_blocks, n_channels, dilation_growth, kernel_size, cond_dim)
+ * dilations[i] = dilation_growth ** i is spelled out so that WaveNet-style
+ * schedules (src/nasr/networks/wavenet.py:159-169) fit the same descriptor.
+ */
+typedef struct nasr_model_desc {
+  int32_t arch;                       /* NASR_ARCH_TCN | NASR_ARCH_GCN                       */
+  int32_t n_blocks;                   /* <= NASR_MAX_BLOCKS                                  */
+  int32_t in_ch, out_ch;
+  int32_t n_channels;                 /* C; GCN conv width is 2C                             */
+  int32_t kernel_size;
+  int32_t cond_dim;
+  int32_t has_film;                   /* TCN: cond_dim > 0 (tcn.py:63-64); GCN: 1 (gcn.py:45) */
+  int32_t final_tanh;                 /* GCN: 1 (gcn.py:145-146); TCN: 0                     */
+  int32_t path;                       /* NASR_PATH_*                                         */
+  float   bn_eps;                     /* 1e-5, nn.BatchNorm1d default                        */
+  int32_t dilations[NASR_MAX_BLOCKS];
+} nasr_model_desc;
+
+typedef struct nasr_engine nasr_engine;
+
+/*
+ * Number of floats nasr_engine_create expects in `weights`, and their order.
+ * Per block i (state_dict keys of the reference module):
+ *   blocks.i.conv.conv.weight [W, Cin, k]   (W = C for TCN, 2C for GCN)
+ *   blocks.i.conv.conv.bias   [W]
+ *   if has_film: blocks.i.film.adaptor.weight [2W, cond_dim], .adaptor.bias [2W],
+ *                blocks.i.film.bn.weight [W], .bn.bias [W],
+ *                .bn.running_mean [W], .bn.running_var [W]
+ *   if TCN:      blocks.i.act.weight [1]
+ *   blocks.i.res.weight [C, Cin]
+ * then out_net.weight [out_ch, C].
+ */
+NASR_API size_t nasr_weight_count(const nasr_model_desc* desc);
+
+/* weights: host pointer, nasr_weight_count(desc) floats. device: CUDA ordinal. */
+NASR_API int nasr_engine_create(const nasr_model_desc* desc, const float* weights_host,
+                       size_t n_weights, int device, nasr_engine** out);
+NASR_API void nasr_engine_destroy(nasr_engine* e);
+
+/* Human-readable text of the last failure on this handle (or of the last
+ * failed nasr_engine_create when e == NULL). Never NULL. */
+NASR_API const char* nasr_last_error(const nasr_engine* e);
+
+/* Fold conv bias + eval BatchNorm + FiLM(cond) into per-(clip, channel)
+ * scale/shift for every block. cond_dev: [B, cond_dim] (may be NULL when
+ * cond_dim == 0). Must precede nasr_forward / nasr_forward_chunk with the same B. */
+NASR_API int nasr_set_cond(nasr_engine* e, const float* cond_dev, int B, void* stream);
+
+/* One-shot forward with zero history (reference TCN/GCN.forward). */
+NASR_API int nasr_forward(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T,
+                 void* stream);
+
+/* nasr_forward with a CUDA-event pair around every block launch on `stream`;
+ * waits for completion and writes the n_blocks device durations (ms) to block_ms.
+ * Used by bench.py for the live per-kernel roofline numbers. */
+NASR_API int nasr_forward_profiled(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T,
+                          void* stream, float* block_ms);
+
+/* Host-buffer forward: H2D(x, cond) -> set_cond -> forward -> D2H(y), all on
+ * `stream`, then waits for completion. cond_host may be NULL when cond_dim == 0. */
+NASR_API int nasr_forward_host(nasr_engine* e, const float* x_host, const float* cond_host,
+                      float* y_host, int B, int64_t T, void* stream);
+
+/* Streaming: per-block history of the last (k-1)*d input rows is carried
+ * across calls (wrapper.py:14-30). reset zero-fills it for B clips. */
+NASR_API int nasr_stream_reset(nasr_engine* e, int B, void* stream);
+NASR_API int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev, int B,
+                       int64_t T_chunk, void* stream);
+
+/* A single block on its own: x [B, Cin, T] -> y [B, C, T] (zero history). */
+NASR_API int nasr_block_forward(nasr_engine* e, int block, const float* x_dev, float* y_dev,
+                       int B, int64_t T, void* stream);
+
+/* Bytes of device workspace the engine holds / would hold for (B, T). */
+NASR_API size_t nasr_workspace_bytes(const nasr_engine* e, int B, int64_t T);
+
+/* Receptive field in samples (tcn.py:157-164, gcn.py:149-160). */
+NASR_API int64_t nasr_receptive_field(const nasr_engine* e);
+
+/* Introspection used by bench.py / tests. */
+NASR_API int64_t nasr_launch_count(const nasr_engine* e);       /* kernels launched by this handle so far   */
+NASR_API int nasr_block_path(const nasr_engine* e, int block);  /* 0 = fp32 FFMA kernel, 1 = tcgen05 kernel */
+NASR_API const char* nasr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NASR_B200_H */

@@ -1,0 +1,181 @@
+"""ctypes binding of libnasr_b200.so (the C ABI in include/nasr_b200.h).
+
+This is the only compute path of the package: if the library is missing or no
+sm_100 device is present, calls raise — there is no CPU / eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+NASR_MAX_BLOCKS = 64
+NASR_OK, NASR_ERR_INVALID, NASR_ERR_CUDA, NASR_ERR_STATE, NASR_ERR_NOMEM = 0, -1, -2, -3, -4
+ARCH_TCN, ARCH_GCN = 0, 1
+PATH_AUTO, PATH_FP32 = 0, 1
+
+LIB_PATH = Path(__file__).resolve().parent / "libnasr_b200.so"
+
+# every symbol include/nasr_b200.h declares
+EXPORTS = (
+    "nasr_weight_count", "nasr_engine_create", "nasr_engine_destroy", "nasr_last_error",
+    "nasr_set_cond", "nasr_forward", "nasr_forward_profiled", "nasr_forward_host", "nasr_stream_reset",
+    "nasr_forward_chunk", "nasr_block_forward", "nasr_workspace_bytes",
+    "nasr_receptive_field", "nasr_launch_count", "nasr_block_path", "nasr_version",
+)
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("arch", C.c_int32), ("n_blocks", C.c_int32), ("in_ch", C.c_int32), ("out_ch", C.c_int32),
+        ("n_channels", C.c_int32), ("kernel_size", C.c_int32), ("cond_dim", C.c_int32),
+        ("has_film", C.c_int32), ("final_tanh", C.c_int32), ("path", C.c_int32),
+        ("bn_eps", C.c_float), ("dilations", C.c_int32 * NASR_MAX_BLOCKS),
+    ]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libnasr_b200.so; raise RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m neural_audio_spring_reverb_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback for the TCN/GCN forward."
+        )
+    lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_LOCAL)
+    vp, i32, i64, f32p = C.c_void_p, C.c_int, C.c_int64, C.c_void_p
+    lib.nasr_weight_count.restype = C.c_size_t
+    lib.nasr_weight_count.argtypes = [C.POINTER(ModelDesc)]
+    lib.nasr_engine_create.restype = i32
+    lib.nasr_engine_create.argtypes = [C.POINTER(ModelDesc), f32p, C.c_size_t, i32, C.POINTER(vp)]
+    lib.nasr_engine_destroy.restype = None
+    lib.nasr_engine_destroy.argtypes = [vp]
+    lib.nasr_last_error.restype = C.c_char_p
+    lib.nasr_last_error.argtypes = [vp]
+    lib.nasr_set_cond.restype = i32
+    lib.nasr_set_cond.argtypes = [vp, f32p, i32, vp]
+    lib.nasr_forward.restype = i32
+    lib.nasr_forward.argtypes = [vp, f32p, f32p, i32, i64, vp]
+    lib.nasr_forward_profiled.restype = i32
+    lib.nasr_forward_profiled.argtypes = [vp, f32p, f32p, i32, i64, vp, C.c_void_p]
+    lib.nasr_forward_host.restype = i32
+    lib.nasr_forward_host.argtypes = [vp, f32p, f32p, f32p, i32, i64, vp]
+    lib.nasr_stream_reset.restype = i32
+    lib.nasr_stream_reset.argtypes = [vp, i32, vp]
+    lib.nasr_forward_chunk.restype = i32
+    lib.nasr_forward_chunk.argtypes = [vp, f32p, f32p, i32, i64, vp]
+    lib.nasr_block_forward.restype = i32
+    lib.nasr_block_forward.argtypes = [vp, i32, f32p, f32p, i32, i64, vp]
+    lib.nasr_workspace_bytes.restype = C.c_size_t
+    lib.nasr_workspace_bytes.argtypes = [vp, i32, i64]
+    lib.nasr_receptive_field.restype = i64
+    lib.nasr_receptive_field.argtypes = [vp]
+    lib.nasr_launch_count.restype = i64
+    lib.nasr_launch_count.argtypes = [vp]
+    lib.nasr_block_path.restype = i32
+    lib.nasr_block_path.argtypes = [vp, i32]
+    lib.nasr_version.restype = C.c_char_p
+    lib.nasr_version.argtypes = []
+    _lib = lib
+    return lib
+
+
+def _raise(lib, handle, code: int, what: str):
+    msg = lib.nasr_last_error(handle).decode("utf-8", "replace")
+    text = f"{what}: {msg} (nasr_status {code})"
+    if code == NASR_ERR_INVALID:
+        raise ValueError(text)
+    if code == NASR_ERR_NOMEM:
+        raise MemoryError(text)
+    raise RuntimeError(text)
+
+
+class Engine:
+    """Owning wrapper of one nasr_engine handle (one device, not thread-safe)."""
+
+    def __init__(self, *, arch: int, n_blocks: int, in_ch: int, out_ch: int, n_channels: int,
+                 kernel_size: int, cond_dim: int, has_film: bool, final_tanh: bool,
+                 dilations, weights, device: int, path: int = PATH_AUTO, bn_eps: float = 1e-5):
+        import numpy as np
+
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        if n_blocks > NASR_MAX_BLOCKS:
+            raise ValueError(f"n_blocks {n_blocks} > {NASR_MAX_BLOCKS}")
+        d = ModelDesc()
+        d.arch, d.n_blocks, d.in_ch, d.out_ch = arch, n_blocks, in_ch, out_ch
+        d.n_channels, d.kernel_size, d.cond_dim = n_channels, kernel_size, cond_dim
+        d.has_film, d.final_tanh, d.path, d.bn_eps = int(has_film), int(final_tanh), path, bn_eps
+        for i, dil in enumerate(dilations):
+            if dil > 2**31 - 1:
+                raise ValueError("dilation does not fit int32")
+            d.dilations[i] = int(dil)
+        self.desc = d
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        rc = self._lib.nasr_engine_create(C.byref(d), w.ctypes.data, w.size, device, C.byref(self._h))
+        if rc != NASR_OK:
+            _raise(self._lib, None, rc, "nasr_engine_create")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.nasr_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int, what: str):
+        if rc != NASR_OK:
+            _raise(self._lib, self._h, rc, what)
+
+    def set_cond(self, cond_ptr: int, B: int, stream: int = 0):
+        self._ck(self._lib.nasr_set_cond(self._h, cond_ptr or None, B, stream or None), "nasr_set_cond")
+
+    def forward(self, x_ptr: int, y_ptr: int, B: int, T: int, stream: int = 0):
+        self._ck(self._lib.nasr_forward(self._h, x_ptr, y_ptr, B, T, stream or None), "nasr_forward")
+
+    def forward_profiled(self, x_ptr: int, y_ptr: int, B: int, T: int, stream: int = 0):
+        """-> list of per-block device milliseconds (CUDA events on `stream`)."""
+        ms = (C.c_float * self.desc.n_blocks)()
+        self._ck(self._lib.nasr_forward_profiled(self._h, x_ptr, y_ptr, B, T, stream or None, ms),
+                 "nasr_forward_profiled")
+        return list(ms)
+
+    def forward_host(self, x_ptr: int, cond_ptr: int, y_ptr: int, B: int, T: int, stream: int = 0):
+        self._ck(self._lib.nasr_forward_host(self._h, x_ptr, cond_ptr or None, y_ptr, B, T, stream or None),
+                 "nasr_forward_host")
+
+    def stream_reset(self, B: int, stream: int = 0):
+        self._ck(self._lib.nasr_stream_reset(self._h, B, stream or None), "nasr_stream_reset")
+
+    def forward_chunk(self, x_ptr: int, y_ptr: int, B: int, T: int, stream: int = 0):
+        self._ck(self._lib.nasr_forward_chunk(self._h, x_ptr, y_ptr, B, T, stream or None), "nasr_forward_chunk")
+
+    def block_forward(self, block: int, x_ptr: int, y_ptr: int, B: int, T: int, stream: int = 0):
+        self._ck(self._lib.nasr_block_forward(self._h, block, x_ptr, y_ptr, B, T, stream or None),
+                 "nasr_block_forward")
+
+    def workspace_bytes(self, B: int, T: int) -> int:
+        return int(self._lib.nasr_workspace_bytes(self._h, B, T))
+
+    def receptive_field(self) -> int:
+        return int(self._lib.nasr_receptive_field(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._lib.nasr_launch_count(self._h))
+
+    def block_path(self, block: int) -> int:
+        return int(self._lib.nasr_block_path(self._h, block))
+
+
+def version() -> str:
+    return load_library().nasr_version().decode()

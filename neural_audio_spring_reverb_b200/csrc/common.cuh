@@ -1,0 +1,86 @@
+// Shared declarations for the libnasr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nasr {
+
+// Activation plane formats.
+//   NCT     : fp32 [B][C][rows]            (reference layout; x, y and single-block I/O)
+//   CL      : fp32 [B][rows][Cp]           (channels-last, Cp = C rounded up to 4)
+//   SPLIT16 : [B][rows][2*Cp] 16-bit       (per row: Cp x fp16 "hi" then Cp x bf16 "lo",
+//                                           value = hi + lo; same bytes as CL fp32;
+//                                           it is the operand format of the tcgen05 kernel)
+//   FINAL   : out_net (1x1, C -> out_ch) [+ tanh] fused; written as NCT fp32
+enum PlaneFmt : int { FMT_NCT = 0, FMT_CL = 1, FMT_SPLIT16 = 2, FMT_FINAL = 3 };
+
+// One fused block launch: causal dilated conv -> folded bias/BN/FiLM affine ->
+// PReLU (TCN) or tanh*sigmoid gate (GCN) -> + 1x1 residual [-> out_net [-> tanh]].
+// Follows TCNBlock.forward (reference src/nasr/networks/tcn.py:73-86) and
+// GCNBlock.forward (gcn.py:53-61).
+struct BlockArgs {
+  const void* in;          // input plane
+  void* out;               // output plane
+  int in_fmt, out_fmt;
+  long long in_clip_stride;   // elements of the plane's scalar type between clips
+  long long out_clip_stride;
+  long long in_rows;          // rows per clip in the input plane (NCT: channel stride)
+  long long out_rows;         // rows per clip in the output plane (NCT/FINAL: channel stride)
+  long long in_row0;          // plane row of sample t = 0 (history prefix length)
+  long long out_row0;
+  int B;
+  long long T;
+  int arch;                // 0 TCN, 1 GCN
+  int Cin, Cinp;           // input channels, padded
+  int W, Wp;               // conv output channels (C or 2C), padded
+  int Cout, Coutp;         // block output channels, padded
+  int k, d;
+  int NC;                  // conv channels per thread in the generic kernel
+  const float* wconv;      // [k][Cinp][Wp]   (GCN: columns grouped per NC, see pack)
+  const float* wres;       // [Cinp][Coutp]
+  const float* scale;      // [B][Wp]  folded FiLM*BN scale (packed column order)
+  const float* shift;      // [B][Wp]
+  float slope;             // PReLU slope (TCN)
+  const float* wout;       // [out_ch][Coutp] (FMT_FINAL)
+  int out_ch;
+  int final_tanh;
+};
+
+cudaError_t launch_generic_block(const BlockArgs& a, int sm_count, cudaStream_t s);
+
+// fold: scale/shift[b][packed(w)] for one block (custom_layers.py:32-42 folded with conv bias)
+struct FoldArgs {
+  const float* cond;       // [B][cond_dim] or nullptr
+  int B, cond_dim, W, Wp, has_film;
+  const float* conv_bias;  // [W]
+  const float* ad_w;       // [2W][cond_dim]
+  const float* ad_b;       // [2W]
+  const float* bn_w; const float* bn_b; const float* bn_mean; const float* bn_var;  // [W]
+  const int* perm;         // [W] original conv channel -> packed column
+  float eps;
+  float* scale; float* shift;  // [B][Wp]
+};
+cudaError_t launch_fold(const FoldArgs* blocks_dev, int n_blocks, int B, int maxW, cudaStream_t s);
+
+// streaming helpers
+cudaError_t launch_copy_rows(const void* src, long long src_clip_stride, long long src_row0,
+                             void* dst, long long dst_clip_stride, long long dst_row0,
+                             long long n_rows, int row_bytes, int B, cudaStream_t s);
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+}  // namespace nasr

@@ -1,0 +1,702 @@
+// libnasr_b200 engine: the C ABI declared in include/nasr_b200.h.
+// Owns packed device weights, folded FiLM scale/shift, activation planes and the
+// streaming history; enqueues one fused block kernel per network block.
+#include "../../include/nasr_b200.h"
+#include "common.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace nasr;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct BlockState {
+  int Cin = 0, Cinp = 0, W = 0, Wp = 0, Cout = 0, Coutp = 0, k = 0, d = 0, NC = 0, path = 0;
+  int in_fmt = FMT_CL, out_fmt = FMT_CL;
+  float slope = 0.f;
+  long long hist = 0;  // (k-1)*d rows of input history (custom_layers.py:71-73)
+  float *wconv = nullptr, *wres = nullptr;
+  float *bias = nullptr, *adw = nullptr, *adb = nullptr, *bnw = nullptr, *bnb = nullptr, *mean = nullptr, *var = nullptr;
+  int* perm = nullptr;
+  float *scale = nullptr, *shift = nullptr;  // [condCap][Wp]
+};
+
+}  // namespace
+
+struct nasr_engine {
+  nasr_model_desc desc{};
+  int device = 0, sm_count = 148;
+  int C = 0, Cp = 0;
+  std::vector<BlockState> blocks;
+  float* wout = nullptr;  // [out_ch][Cp]
+  FoldArgs* fold_dev = nullptr;
+  int condCap = 0, condB = 0;
+  DevBuf plane[2];
+  // streaming
+  int streamB = 0;
+  long long streamTcap = 0;
+  std::vector<DevBuf> splane;
+  DevBuf scratch;
+  // host path
+  DevBuf hx, hy, hc;
+  size_t budget_bytes = (size_t)24 << 30;
+  mutable std::string err;
+  int64_t launches = 0;
+};
+
+namespace {
+
+int fail(nasr_engine* e, int code, const std::string& msg) {
+  if (e) e->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define NASR_CUDA(e, call)                                                              \
+  do {                                                                                  \
+    cudaError_t _err = (call);                                                          \
+    if (_err != cudaSuccess)                                                            \
+      return fail((e), _err == cudaErrorMemoryAllocation ? NASR_ERR_NOMEM : NASR_ERR_CUDA, \
+                  std::string(#call) + ": " + cudaGetErrorString(_err));                \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+cudaError_t ensure(DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return cudaSuccess;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  cudaError_t err = cudaMalloc(&b.p, bytes);
+  if (err == cudaSuccess) b.cap = bytes;
+  return err;
+}
+
+void release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+template <typename T>
+cudaError_t upload(T** dst, const std::vector<T>& host) {
+  cudaError_t err = cudaMalloc((void**)dst, host.size() * sizeof(T) + 16);
+  if (err != cudaSuccess) return err;
+  return cudaMemcpy(*dst, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+size_t block_weight_count(const nasr_model_desc& d, int i) {
+  const size_t C = d.n_channels, Cin = (i == 0) ? d.in_ch : d.n_channels;
+  const size_t W = (d.arch == NASR_ARCH_GCN) ? 2 * C : C;
+  size_t n = W * Cin * d.kernel_size + W;
+  if (d.has_film) n += 2 * W * d.cond_dim + 2 * W + 4 * W;
+  if (d.arch == NASR_ARCH_TCN) n += 1;
+  n += C * Cin;
+  return n;
+}
+
+int validate(const nasr_model_desc* d, std::string& why) {
+  if (!d) { why = "desc is NULL"; return 0; }
+  if (d->arch != NASR_ARCH_TCN && d->arch != NASR_ARCH_GCN) { why = "arch must be TCN(0) or GCN(1)"; return 0; }
+  if (d->n_blocks < 1 || d->n_blocks > NASR_MAX_BLOCKS) { why = "n_blocks out of range [1,64]"; return 0; }
+  if (d->in_ch < 1 || d->out_ch < 1 || d->n_channels < 1 || d->kernel_size < 1 || d->cond_dim < 0) {
+    why = "in_ch, out_ch, n_channels, kernel_size must be >= 1 and cond_dim >= 0"; return 0;
+  }
+  if (d->arch == NASR_ARCH_GCN && !d->has_film) { why = "GCN always carries FiLM (gcn.py:45)"; return 0; }
+  for (int i = 0; i < d->n_blocks; ++i)
+    if (d->dilations[i] < 1) { why = "dilations must be >= 1"; return 0; }
+  const int Cp = round_up(d->n_channels, 4);
+  if (d->arch == NASR_ARCH_TCN && Cp > 256) { why = "TCN n_channels > 256 unsupported"; return 0; }
+  if (d->arch == NASR_ARCH_GCN && Cp > 128) { why = "GCN n_channels > 128 unsupported"; return 0; }
+  if (d->in_ch > 64 || d->out_ch > 16) { why = "in_ch > 64 or out_ch > 16 unsupported"; return 0; }
+  return 1;
+}
+
+int pick_nc(int arch, int Cp) {
+  if (arch == NASR_ARCH_TCN) {
+    if (Cp % 16 == 0 && Cp >= 128) return 16;
+    if (Cp % 8 == 0 && Cp >= 32) return 8;
+    return 4;
+  }
+  if (Cp % 8 == 0 && Cp >= 128) return 16;
+  return 8;
+}
+
+void free_block(BlockState& b) {
+  float** fp[] = {&b.wconv, &b.wres, &b.bias, &b.adw, &b.adb, &b.bnw, &b.bnb, &b.mean, &b.var, &b.scale, &b.shift};
+  for (float** p : fp) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  if (b.perm) cudaFree(b.perm);
+  b.perm = nullptr;
+}
+
+BlockArgs make_args(const nasr_engine* e, int i, int B) {
+  const BlockState& bs = e->blocks[i];
+  BlockArgs a{};
+  a.B = B;
+  a.arch = e->desc.arch;
+  a.Cin = bs.Cin; a.Cinp = bs.Cinp; a.W = bs.W; a.Wp = bs.Wp; a.Cout = bs.Cout; a.Coutp = bs.Coutp;
+  a.k = bs.k; a.d = bs.d; a.NC = bs.NC;
+  a.wconv = bs.wconv; a.wres = bs.wres; a.scale = bs.scale; a.shift = bs.shift;
+  a.slope = bs.slope;
+  a.wout = e->wout; a.out_ch = e->desc.out_ch; a.final_tanh = e->desc.final_tanh;
+  a.in_fmt = bs.in_fmt; a.out_fmt = bs.out_fmt;
+  return a;
+}
+
+int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s) {
+  cudaError_t err = launch_generic_block(a, e->sm_count, s);
+  if (err != cudaSuccess)
+    return fail(e, err == cudaErrorInvalidConfiguration ? NASR_ERR_INVALID : NASR_ERR_CUDA,
+                "block " + std::to_string(i) + " launch: " + cudaGetErrorString(err));
+  e->launches += 1;
+  return NASR_OK;
+}
+
+// bytes of one activation plane row (CL fp32 and SPLIT16 are the same size)
+inline size_t plane_row_bytes(const nasr_engine* e) { return (size_t)e->Cp * 4; }
+
+}  // namespace
+
+extern "C" {
+
+const char* nasr_version(void) { return "nasr_b200 0.1.0 (sm_100a)"; }
+
+size_t nasr_weight_count(const nasr_model_desc* d) {
+  std::string why;
+  if (!validate(d, why)) return 0;
+  size_t n = 0;
+  for (int i = 0; i < d->n_blocks; ++i) n += block_weight_count(*d, i);
+  return n + (size_t)d->out_ch * d->n_channels;
+}
+
+const char* nasr_last_error(const nasr_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+void nasr_engine_destroy(nasr_engine* e) {
+  if (!e) return;
+  {
+    DeviceGuard g(e->device);
+    for (auto& b : e->blocks) free_block(b);
+    if (e->wout) cudaFree(e->wout);
+    if (e->fold_dev) cudaFree(e->fold_dev);
+    release(e->plane[0]); release(e->plane[1]);
+    for (auto& p : e->splane) release(p);
+    release(e->scratch); release(e->hx); release(e->hy); release(e->hc);
+  }
+  delete e;
+}
+
+int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_weights, int device,
+                       nasr_engine** out) {
+  if (!out) return fail(nullptr, NASR_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  std::string why;
+  if (!validate(desc, why)) return fail(nullptr, NASR_ERR_INVALID, why);
+  if (!w) return fail(nullptr, NASR_ERR_INVALID, "weights is NULL");
+  if (n_weights != nasr_weight_count(desc))
+    return fail(nullptr, NASR_ERR_INVALID, "weight blob has " + std::to_string(n_weights) + " floats, expected " +
+                                               std::to_string(nasr_weight_count(desc)));
+  int ndev = 0;
+  cudaError_t cerr = cudaGetDeviceCount(&ndev);
+  if (cerr != cudaSuccess || ndev == 0)
+    return fail(nullptr, NASR_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") +
+                                            cudaGetErrorString(cerr));
+  if (device < 0 || device >= ndev) return fail(nullptr, NASR_ERR_INVALID, "device ordinal out of range");
+  cudaDeviceProp prop{};
+  NASR_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, NASR_ERR_CUDA, std::string("libnasr_b200 is built for sm_100a only; device is sm_") +
+                                            std::to_string(prop.major) + std::to_string(prop.minor));
+
+  nasr_engine* e = new (std::nothrow) nasr_engine();
+  if (!e) return fail(nullptr, NASR_ERR_NOMEM, "host allocation failed");
+  e->desc = *desc;
+  e->device = device;
+  e->sm_count = prop.multiProcessorCount;
+  e->C = desc->n_channels;
+  e->Cp = round_up(desc->n_channels, 4);
+  if (const char* env = getenv("NASR_WORKSPACE_MB")) {
+    const long long mb = atoll(env);
+    if (mb > 0) e->budget_bytes = (size_t)mb << 20;
+  }
+  DeviceGuard guard(device);
+
+  const int n = desc->n_blocks, C = e->C, Cp = e->Cp, k = desc->kernel_size, cd = desc->cond_dim;
+  const bool gcn = desc->arch == NASR_ARCH_GCN;
+  e->blocks.resize(n);
+  const float* p = w;
+  std::vector<FoldArgs> fold(n);
+  int rc = NASR_OK;
+  auto up = [&](auto** dst, const auto& host) {
+    if (rc != NASR_OK) return;
+    cudaError_t err = upload(dst, host);
+    if (err != cudaSuccess) rc = fail(nullptr, NASR_ERR_CUDA, std::string("weight upload: ") + cudaGetErrorString(err));
+  };
+  for (int i = 0; i < n; ++i) {
+    BlockState& b = e->blocks[i];
+    b.Cin = (i == 0) ? desc->in_ch : C;
+    b.Cinp = (i == 0) ? desc->in_ch : Cp;
+    b.W = gcn ? 2 * C : C;
+    b.Wp = gcn ? 2 * Cp : Cp;
+    b.Cout = C; b.Coutp = Cp;
+    b.k = k; b.d = desc->dilations[i];
+    b.hist = (long long)(k - 1) * b.d;
+    b.NC = pick_nc(desc->arch, Cp);
+    b.path = 0;
+    b.in_fmt = (i == 0) ? FMT_NCT : FMT_CL;
+    b.out_fmt = (i == n - 1) ? FMT_FINAL : FMT_CL;
+    if (b.Wp / b.NC > 16) { rc = fail(nullptr, NASR_ERR_INVALID, "channel count too large for the generic kernel"); break; }
+
+    // permutation: original conv channel -> packed column (GCN: tanh/sigmoid halves
+    // of the same output channel group land in one thread, custom_layers.py:103-111)
+    std::vector<int> perm(b.W);
+    if (!gcn) {
+      for (int c = 0; c < b.W; ++c) perm[c] = c;
+    } else {
+      const int h = b.NC / 2;
+      for (int c = 0; c < C; ++c) {
+        const int g = c / h, j = c % h;
+        perm[c] = g * b.NC + j;
+        perm[C + c] = g * b.NC + h + j;
+      }
+    }
+    const float* conv_w = p; p += (size_t)b.W * b.Cin * k;
+    const float* conv_b = p; p += b.W;
+    std::vector<float> h_bias(conv_b, conv_b + b.W);
+    std::vector<float> h_adw, h_adb, h_bnw, h_bnb, h_mean, h_var;
+    if (desc->has_film) {
+      h_adw.assign(p, p + (size_t)2 * b.W * cd); p += (size_t)2 * b.W * cd;
+      h_adb.assign(p, p + 2 * b.W); p += 2 * b.W;
+      h_bnw.assign(p, p + b.W); p += b.W;
+      h_bnb.assign(p, p + b.W); p += b.W;
+      h_mean.assign(p, p + b.W); p += b.W;
+      h_var.assign(p, p + b.W); p += b.W;
+    }
+    if (!gcn) { b.slope = *p; p += 1; }
+    const float* res_w = p; p += (size_t)C * b.Cin;
+
+    std::vector<float> h_wconv((size_t)k * b.Cinp * b.Wp, 0.f);
+    for (int co = 0; co < b.W; ++co)
+      for (int ci = 0; ci < b.Cin; ++ci)
+        for (int j = 0; j < k; ++j)
+          h_wconv[((size_t)j * b.Cinp + ci) * b.Wp + perm[co]] = conv_w[((size_t)co * b.Cin + ci) * k + j];
+    std::vector<float> h_wres((size_t)b.Cinp * b.Coutp, 0.f);
+    for (int co = 0; co < C; ++co)
+      for (int ci = 0; ci < b.Cin; ++ci) h_wres[(size_t)ci * b.Coutp + co] = res_w[(size_t)co * b.Cin + ci];
+
+    up(&b.wconv, h_wconv); up(&b.wres, h_wres); up(&b.bias, h_bias); up(&b.perm, perm);
+    if (desc->has_film) {
+      if (h_adw.empty()) h_adw.push_back(0.f);  // cond_dim == 0: Linear(0, 2W) is bias only
+      up(&b.adw, h_adw); up(&b.adb, h_adb); up(&b.bnw, h_bnw); up(&b.bnb, h_bnb); up(&b.mean, h_mean); up(&b.var, h_var);
+    }
+    if (rc != NASR_OK) break;
+  }
+  if (rc == NASR_OK) {
+    std::vector<float> h_wout((size_t)desc->out_ch * Cp, 0.f);
+    for (int o = 0; o < desc->out_ch; ++o)
+      for (int c = 0; c < C; ++c) h_wout[(size_t)o * Cp + c] = p[(size_t)o * C + c];
+    up(&e->wout, h_wout);
+  }
+  if (rc == NASR_OK) {
+    cudaError_t err = cudaMalloc((void**)&e->fold_dev, sizeof(FoldArgs) * n);
+    if (err != cudaSuccess) rc = fail(nullptr, NASR_ERR_NOMEM, "fold args allocation failed");
+  }
+  if (rc != NASR_OK) {
+    std::string keep = g_create_error;
+    nasr_engine_destroy(e);
+    g_create_error = keep;
+    return rc;
+  }
+  *out = e;
+  return NASR_OK;
+}
+
+int nasr_set_cond(nasr_engine* e, const float* cond_dev, int B, void* stream) {
+  if (!e) return NASR_ERR_INVALID;
+  if (B < 1) return fail(e, NASR_ERR_INVALID, "B must be >= 1");
+  if (e->desc.has_film && e->desc.cond_dim > 0 && !cond_dev)
+    return fail(e, NASR_ERR_INVALID, "cond is NULL but cond_dim > 0");
+  DeviceGuard guard(e->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = (int)e->blocks.size();
+  if (B > e->condCap) {
+    // grow scale/shift; in-flight work on other streams must not still be reading them
+    NASR_CUDA(e, cudaDeviceSynchronize());
+    for (auto& b : e->blocks) {
+      if (b.scale) cudaFree(b.scale);
+      if (b.shift) cudaFree(b.shift);
+      b.scale = b.shift = nullptr;
+      NASR_CUDA(e, cudaMalloc((void**)&b.scale, (size_t)B * b.Wp * sizeof(float)));
+      NASR_CUDA(e, cudaMalloc((void**)&b.shift, (size_t)B * b.Wp * sizeof(float)));
+      NASR_CUDA(e, cudaMemset(b.scale, 0, (size_t)B * b.Wp * sizeof(float)));
+      NASR_CUDA(e, cudaMemset(b.shift, 0, (size_t)B * b.Wp * sizeof(float)));
+    }
+    e->condCap = B;
+  }
+  std::vector<FoldArgs> fold(n);
+  int maxW = 0;
+  for (int i = 0; i < n; ++i) {
+    const BlockState& b = e->blocks[i];
+    FoldArgs& f = fold[i];
+    f.cond = cond_dev; f.B = B; f.cond_dim = e->desc.cond_dim; f.W = b.W; f.Wp = b.Wp; f.has_film = e->desc.has_film;
+    f.conv_bias = b.bias; f.ad_w = b.adw; f.ad_b = b.adb; f.bn_w = b.bnw; f.bn_b = b.bnb; f.bn_mean = b.mean; f.bn_var = b.var;
+    f.perm = b.perm; f.eps = e->desc.bn_eps; f.scale = b.scale; f.shift = b.shift;
+    if (b.W > maxW) maxW = b.W;
+  }
+  NASR_CUDA(e, cudaMemcpyAsync(e->fold_dev, fold.data(), sizeof(FoldArgs) * n, cudaMemcpyHostToDevice, s));
+  // the pageable staging copy above completes before return for non-pinned memory
+  NASR_CUDA(e, launch_fold(e->fold_dev, n, B, maxW, s));
+  e->launches += 1;
+  e->condB = B;
+  return NASR_OK;
+}
+
+static int forward_slice(nasr_engine* e, const float* x, float* y, int b0, int B, int64_t T, cudaStream_t s,
+                         cudaEvent_t* ev = nullptr) {
+  const int n = (int)e->blocks.size();
+  const size_t row_bytes = plane_row_bytes(e);
+  const long long plane_elems = (long long)T * e->Cp;  // fp32 elements per clip
+  for (int i = 0; i < n; ++i) {
+    const BlockState& bs = e->blocks[i];
+    BlockArgs a = make_args(e, i, B);
+    a.T = T;
+    a.scale = bs.scale + (size_t)b0 * bs.Wp;
+    a.shift = bs.shift + (size_t)b0 * bs.Wp;
+    if (i == 0) {
+      a.in = x; a.in_clip_stride = (long long)e->desc.in_ch * T; a.in_rows = T; a.in_row0 = 0;
+    } else {
+      a.in = e->plane[(i - 1) & 1].p;
+      a.in_clip_stride = (bs.in_fmt == FMT_SPLIT16) ? plane_elems * 2 : plane_elems;
+      a.in_rows = T; a.in_row0 = 0;
+    }
+    if (i == n - 1) {
+      a.out = y; a.out_clip_stride = (long long)e->desc.out_ch * T; a.out_rows = T; a.out_row0 = 0;
+    } else {
+      a.out = e->plane[i & 1].p;
+      a.out_clip_stride = (bs.out_fmt == FMT_SPLIT16) ? plane_elems * 2 : plane_elems;
+      a.out_rows = T; a.out_row0 = 0;
+    }
+    if (ev) cudaEventRecord(ev[i], s);
+    int rc = launch_block(e, a, i, s);
+    if (rc != NASR_OK) return rc;
+  }
+  if (ev) cudaEventRecord(ev[n], s);
+  (void)row_bytes;
+  return NASR_OK;
+}
+
+static int forward_impl(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T, void* stream,
+                        float* block_ms);
+
+int nasr_forward(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T, void* stream) {
+  return forward_impl(e, x_dev, y_dev, B, T, stream, nullptr);
+}
+
+int nasr_forward_profiled(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T, void* stream,
+                          float* block_ms) {
+  if (!block_ms) return e ? fail(e, NASR_ERR_INVALID, "block_ms is NULL") : NASR_ERR_INVALID;
+  return forward_impl(e, x_dev, y_dev, B, T, stream, block_ms);
+}
+
+static int forward_impl(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T, void* stream,
+                        float* block_ms) {
+  if (!e) return NASR_ERR_INVALID;
+  if (!x_dev || !y_dev) return fail(e, NASR_ERR_INVALID, "x or y is NULL");
+  if (B < 1 || T < 0) return fail(e, NASR_ERR_INVALID, "B must be >= 1 and T >= 0");
+  if (T == 0) return NASR_OK;
+  DeviceGuard guard(e->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (e->condB != B) {
+    if (e->desc.has_film && e->desc.cond_dim > 0)
+      return fail(e, NASR_ERR_STATE, "nasr_set_cond must be called with the same B before nasr_forward");
+    int rc = nasr_set_cond(e, nullptr, B, stream);
+    if (rc != NASR_OK) return rc;
+  }
+  const int n = (int)e->blocks.size();
+  const size_t per_clip = (size_t)T * plane_row_bytes(e);
+  const int nplanes = n >= 3 ? 2 : (n == 2 ? 1 : 0);
+  int slice = B;
+  if (nplanes > 0) {
+    const size_t fit = e->budget_bytes / (per_clip * nplanes);
+    if (fit < 1) {
+      // one clip does not fit the workspace budget: still try, cudaMalloc decides
+      slice = 1;
+    } else if ((size_t)slice > fit) {
+      slice = (int)fit;
+    }
+    for (int q = 0; q < nplanes; ++q) {
+      if (e->plane[q].cap < per_clip * slice) {
+        NASR_CUDA(e, cudaStreamSynchronize(s));
+        NASR_CUDA(e, ensure(e->plane[q], per_clip * slice));
+      }
+    }
+  }
+  std::vector<cudaEvent_t> ev;
+  if (block_ms) {
+    ev.resize(n + 1);
+    for (auto& q : ev) NASR_CUDA(e, cudaEventCreate(&q));
+    for (int i = 0; i < n; ++i) block_ms[i] = 0.f;
+  }
+  int rc = NASR_OK;
+  for (int b0 = 0; b0 < B && rc == NASR_OK; b0 += slice) {
+    const int nb = (B - b0 < slice) ? B - b0 : slice;
+    rc = forward_slice(e, x_dev + (size_t)b0 * e->desc.in_ch * T, y_dev + (size_t)b0 * e->desc.out_ch * T, b0, nb, T, s,
+                       block_ms ? ev.data() : nullptr);
+    if (block_ms && rc == NASR_OK) {
+      if (cudaEventSynchronize(ev[n]) != cudaSuccess) rc = fail(e, NASR_ERR_CUDA, "event synchronize failed");
+      for (int i = 0; i < n && rc == NASR_OK; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+        block_ms[i] += ms;
+      }
+    }
+  }
+  for (auto& q : ev) cudaEventDestroy(q);
+  return rc;
+}
+
+int nasr_forward_host(nasr_engine* e, const float* x_host, const float* cond_host, float* y_host, int B, int64_t T,
+                      void* stream) {
+  if (!e) return NASR_ERR_INVALID;
+  if (!x_host || !y_host) return fail(e, NASR_ERR_INVALID, "x or y is NULL");
+  if (B < 1 || T < 0) return fail(e, NASR_ERR_INVALID, "B must be >= 1 and T >= 0");
+  const int cd = e->desc.cond_dim;
+  if (e->desc.has_film && cd > 0 && !cond_host) return fail(e, NASR_ERR_INVALID, "cond is NULL but cond_dim > 0");
+  if (T == 0) return NASR_OK;
+  DeviceGuard guard(e->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t xb = (size_t)B * e->desc.in_ch * T * sizeof(float);
+  const size_t yb = (size_t)B * e->desc.out_ch * T * sizeof(float);
+  if (e->hx.cap < xb || e->hy.cap < yb) NASR_CUDA(e, cudaStreamSynchronize(s));
+  NASR_CUDA(e, ensure(e->hx, xb));
+  NASR_CUDA(e, ensure(e->hy, yb));
+  NASR_CUDA(e, cudaMemcpyAsync(e->hx.p, x_host, xb, cudaMemcpyHostToDevice, s));
+  const float* cdev = nullptr;
+  if (cd > 0 && cond_host) {
+    NASR_CUDA(e, ensure(e->hc, (size_t)B * cd * sizeof(float)));
+    NASR_CUDA(e, cudaMemcpyAsync(e->hc.p, cond_host, (size_t)B * cd * sizeof(float), cudaMemcpyHostToDevice, s));
+    cdev = (const float*)e->hc.p;
+  }
+  int rc = nasr_set_cond(e, cdev, B, stream);
+  if (rc != NASR_OK) return rc;
+  rc = nasr_forward(e, (const float*)e->hx.p, (float*)e->hy.p, B, T, stream);
+  if (rc != NASR_OK) return rc;
+  NASR_CUDA(e, cudaMemcpyAsync(y_host, e->hy.p, yb, cudaMemcpyDeviceToHost, s));
+  NASR_CUDA(e, cudaStreamSynchronize(s));
+  return NASR_OK;
+}
+
+// ---- streaming (wrapper.py:14-57): plane i = input of block i, laid out as
+// [hist_i rows of history][chunk rows]; after a chunk the last hist_i rows move
+// to the front, exactly PaddingCached's  pad_buf = cat([pad_buf, x])[..., -padding:] ----
+
+static size_t splane_bytes(const nasr_engine* e, int i, int B, long long Tcap) {
+  const BlockState& b = e->blocks[i];
+  if (i == 0) return (size_t)B * e->desc.in_ch * (b.hist + Tcap) * sizeof(float);
+  return (size_t)B * (b.hist + Tcap) * plane_row_bytes(e);
+}
+
+static int stream_alloc(nasr_engine* e, int B, long long Tcap, cudaStream_t s, bool keep_history) {
+  const int n = (int)e->blocks.size();
+  std::vector<DevBuf> np(n);
+  for (int i = 0; i < n; ++i) {
+    cudaError_t err = ensure(np[i], splane_bytes(e, i, B, Tcap));
+    if (err != cudaSuccess) {
+      for (auto& q : np) release(q);
+      return fail(e, NASR_ERR_NOMEM, std::string("stream plane allocation: ") + cudaGetErrorString(err));
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    const BlockState& b = e->blocks[i];
+    if (b.hist == 0) continue;
+    if (i == 0) {
+      const long long old_rows = b.hist + e->streamTcap, new_rows = b.hist + Tcap;
+      if (keep_history)
+        NASR_CUDA(e, launch_copy_rows(e->splane[i].p, old_rows * 4, 0, np[i].p, new_rows * 4, 0, b.hist, 4,
+                                      B * e->desc.in_ch, s));
+      else
+        NASR_CUDA(e, cudaMemsetAsync(np[i].p, 0, np[i].cap, s));
+    } else {
+      const long long rb = (long long)plane_row_bytes(e);
+      const long long old_rows = b.hist + e->streamTcap, new_rows = b.hist + Tcap;
+      if (keep_history)
+        NASR_CUDA(e, launch_copy_rows(e->splane[i].p, old_rows * rb, 0, np[i].p, new_rows * rb, 0, b.hist, (int)rb, B, s));
+      else
+        NASR_CUDA(e, cudaMemsetAsync(np[i].p, 0, np[i].cap, s));
+    }
+    if (keep_history) e->launches += 1;
+  }
+  NASR_CUDA(e, cudaStreamSynchronize(s));
+  for (auto& q : e->splane) release(q);
+  e->splane = np;
+  e->streamB = B;
+  e->streamTcap = Tcap;
+  return NASR_OK;
+}
+
+int nasr_stream_reset(nasr_engine* e, int B, void* stream) {
+  if (!e) return NASR_ERR_INVALID;
+  if (B < 1) return fail(e, NASR_ERR_INVALID, "B must be >= 1");
+  DeviceGuard guard(e->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long Tcap = (e->streamB == B && e->streamTcap > 0) ? e->streamTcap : 1024;
+  if (e->streamB == B && !e->splane.empty()) {
+    for (auto& q : e->splane) NASR_CUDA(e, cudaMemsetAsync(q.p, 0, q.cap, s));
+    return NASR_OK;
+  }
+  return stream_alloc(e, B, Tcap, s, false);
+}
+
+int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t Tc, void* stream) {
+  if (!e) return NASR_ERR_INVALID;
+  if (!x_dev || !y_dev) return fail(e, NASR_ERR_INVALID, "x or y is NULL");
+  if (B < 1 || Tc < 0) return fail(e, NASR_ERR_INVALID, "B must be >= 1 and T_chunk >= 0");
+  if (e->streamB != B || e->splane.empty())
+    return fail(e, NASR_ERR_STATE, "nasr_stream_reset(B) must precede nasr_forward_chunk");
+  if (Tc == 0) return NASR_OK;
+  DeviceGuard guard(e->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (e->condB != B) {
+    if (e->desc.has_film && e->desc.cond_dim > 0)
+      return fail(e, NASR_ERR_STATE, "nasr_set_cond must be called with the same B before nasr_forward_chunk");
+    int rc = nasr_set_cond(e, nullptr, B, stream);
+    if (rc != NASR_OK) return rc;
+  }
+  if (Tc > e->streamTcap) {
+    int rc = stream_alloc(e, B, Tc, s, true);
+    if (rc != NASR_OK) return rc;
+  }
+  const int n = (int)e->blocks.size();
+  const long long Tcap = e->streamTcap;
+  const long long rb = (long long)plane_row_bytes(e);
+  const int in_ch = e->desc.in_ch;
+  // stage the chunk behind block 0's history
+  {
+    const BlockState& b0 = e->blocks[0];
+    NASR_CUDA(e, launch_copy_rows(x_dev, Tc * 4, 0, e->splane[0].p, (b0.hist + Tcap) * 4, b0.hist, Tc, 4, B * in_ch, s));
+    e->launches += 1;
+  }
+  for (int i = 0; i < n; ++i) {
+    const BlockState& bs = e->blocks[i];
+    BlockArgs a = make_args(e, i, B);
+    a.T = Tc;
+    a.in = e->splane[i].p;
+    a.in_row0 = bs.hist;
+    if (i == 0) {
+      a.in_rows = bs.hist + Tcap; a.in_clip_stride = (long long)in_ch * a.in_rows;
+    } else {
+      a.in_rows = bs.hist + Tcap;
+      a.in_clip_stride = a.in_rows * e->Cp * (bs.in_fmt == FMT_SPLIT16 ? 2 : 1);
+    }
+    if (i == n - 1) {
+      a.out = y_dev; a.out_clip_stride = (long long)e->desc.out_ch * Tc; a.out_rows = Tc; a.out_row0 = 0;
+    } else {
+      const BlockState& nx = e->blocks[i + 1];
+      a.out = e->splane[i + 1].p;
+      a.out_rows = nx.hist + Tcap; a.out_row0 = nx.hist;
+      a.out_clip_stride = a.out_rows * e->Cp * (bs.out_fmt == FMT_SPLIT16 ? 2 : 1);
+    }
+    int rc = launch_block(e, a, i, s);
+    if (rc != NASR_OK) return rc;
+  }
+  // carry: rows [Tc, Tc + hist) -> [0, hist) of every plane
+  for (int i = 0; i < n; ++i) {
+    const BlockState& bs = e->blocks[i];
+    if (bs.hist == 0) continue;
+    const long long rows = bs.hist + Tcap;
+    const long long stride = (i == 0) ? rows * 4 : rows * rb;
+    const int rbytes = (i == 0) ? 4 : (int)rb;
+    const int segs = (i == 0) ? B * in_ch : B;
+    if (Tc >= bs.hist) {
+      NASR_CUDA(e, launch_copy_rows(e->splane[i].p, stride, Tc, e->splane[i].p, stride, 0, bs.hist, rbytes, segs, s));
+      e->launches += 1;
+    } else {
+      const size_t need = (size_t)segs * bs.hist * rbytes;
+      if (e->scratch.cap < need) {
+        NASR_CUDA(e, cudaStreamSynchronize(s));
+        NASR_CUDA(e, ensure(e->scratch, need));
+      }
+      NASR_CUDA(e, launch_copy_rows(e->splane[i].p, stride, Tc, e->scratch.p, bs.hist * rbytes, 0, bs.hist, rbytes, segs, s));
+      NASR_CUDA(e, launch_copy_rows(e->scratch.p, bs.hist * rbytes, 0, e->splane[i].p, stride, 0, bs.hist, rbytes, segs, s));
+      e->launches += 2;
+    }
+  }
+  return NASR_OK;
+}
+
+int nasr_block_forward(nasr_engine* e, int block, const float* x_dev, float* y_dev, int B, int64_t T, void* stream) {
+  if (!e) return NASR_ERR_INVALID;
+  if (block < 0 || block >= (int)e->blocks.size()) return fail(e, NASR_ERR_INVALID, "block index out of range");
+  if (!x_dev || !y_dev) return fail(e, NASR_ERR_INVALID, "x or y is NULL");
+  if (B < 1 || T < 0) return fail(e, NASR_ERR_INVALID, "B must be >= 1 and T >= 0");
+  if (T == 0) return NASR_OK;
+  DeviceGuard guard(e->device);
+  if (e->condB != B) {
+    if (e->desc.has_film && e->desc.cond_dim > 0)
+      return fail(e, NASR_ERR_STATE, "nasr_set_cond must be called with the same B before nasr_block_forward");
+    int rc = nasr_set_cond(e, nullptr, B, stream);
+    if (rc != NASR_OK) return rc;
+  }
+  const BlockState& bs = e->blocks[block];
+  BlockArgs a = make_args(e, block, B);
+  a.T = T;
+  a.in_fmt = FMT_NCT; a.out_fmt = FMT_NCT;
+  a.in = x_dev; a.in_clip_stride = (long long)bs.Cin * T; a.in_rows = T; a.in_row0 = 0;
+  a.out = y_dev; a.out_clip_stride = (long long)bs.Cout * T; a.out_rows = T; a.out_row0 = 0;
+  return launch_block(e, a, block, (cudaStream_t)stream);
+}
+
+size_t nasr_workspace_bytes(const nasr_engine* e, int B, int64_t T) {
+  if (!e || B < 1 || T < 1) return 0;
+  const int n = (int)e->blocks.size();
+  const int nplanes = n >= 3 ? 2 : (n == 2 ? 1 : 0);
+  size_t per_clip = (size_t)T * plane_row_bytes(e);
+  size_t want = per_clip * (size_t)B * nplanes;
+  if (want > e->budget_bytes && nplanes > 0) {
+    size_t fit = e->budget_bytes / (per_clip * nplanes);
+    if (fit < 1) fit = 1;
+    want = per_clip * fit * nplanes;
+  }
+  return want;
+}
+
+int64_t nasr_receptive_field(const nasr_engine* e) {
+  if (!e) return 0;
+  int64_t rf = e->desc.kernel_size;
+  for (int i = 1; i < e->desc.n_blocks; ++i) rf += (int64_t)(e->desc.kernel_size - 1) * e->desc.dilations[i];
+  return rf;
+}
+
+int64_t nasr_launch_count(const nasr_engine* e) { return e ? e->launches : 0; }
+
+int nasr_block_path(const nasr_engine* e, int block) {
+  if (!e || block < 0 || block >= (int)e->blocks.size()) return -1;
+  return e->blocks[block].path;
+}
+
+}  // extern "C"

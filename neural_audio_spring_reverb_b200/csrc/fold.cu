@@ -1,0 +1,83 @@
+// Small helper kernels: FiLM/BatchNorm/bias fold (K4) and plane row copies
+// used by the streaming state carry (K5).
+#include "common.cuh"
+
+namespace nasr {
+
+// FiLM.forward (reference src/nasr/networks/custom_layers.py:32-42) applied to
+// conv(x) + bias (custom_layers.py:85-88) in eval mode is, per (clip b, channel w),
+//   y = conv * scale + shift
+//   g    = adaptor(cond)[w],  beta = adaptor(cond)[W + w]          (chunk(2), g first)
+//   inv  = bn.weight[w] / sqrt(bn.running_var[w] + eps)
+//   scale = g * inv
+//   shift = g * ((bias[w] - bn.running_mean[w]) * inv + bn.bias[w]) + beta
+// Without FiLM (TCN with cond_dim == 0, tcn.py:63-64): scale = 1, shift = bias.
+// Computed in fp64 and rounded once.
+__global__ void fold_kernel(const FoldArgs* __restrict__ blocks) {
+  const FoldArgs f = blocks[blockIdx.x];
+  const int b = blockIdx.y;
+  for (int w = threadIdx.x; w < f.W; w += blockDim.x) {
+    double scale = 1.0, shift = (double)f.conv_bias[w];
+    if (f.has_film) {
+      double g = (double)f.ad_b[w], beta = (double)f.ad_b[f.W + w];
+      for (int q = 0; q < f.cond_dim; ++q) {
+        const double c = (double)f.cond[(long long)b * f.cond_dim + q];
+        g += (double)f.ad_w[(long long)w * f.cond_dim + q] * c;
+        beta += (double)f.ad_w[(long long)(f.W + w) * f.cond_dim + q] * c;
+      }
+      const double inv = (double)f.bn_w[w] / sqrt((double)f.bn_var[w] + (double)f.eps);
+      scale = g * inv;
+      shift = g * (((double)f.conv_bias[w] - (double)f.bn_mean[w]) * inv + (double)f.bn_b[w]) + beta;
+    }
+    const int p = f.perm[w];
+    f.scale[(long long)b * f.Wp + p] = (float)scale;
+    f.shift[(long long)b * f.Wp + p] = (float)shift;
+  }
+}
+
+cudaError_t launch_fold(const FoldArgs* blocks_dev, int n_blocks, int B, int maxW, cudaStream_t s) {
+  if (n_blocks <= 0 || B <= 0) return cudaSuccess;
+  int threads = 32;
+  while (threads < maxW && threads < 256) threads <<= 1;
+  fold_kernel<<<dim3(n_blocks, B), threads, 0, s>>>(blocks_dev);
+  return cudaGetLastError();
+}
+
+// copy `n_bytes` contiguous bytes for each of `count` segments
+__global__ void copy_segments_kernel(const char* __restrict__ src, long long src_stride,
+                                     char* __restrict__ dst, long long dst_stride,
+                                     long long n_bytes, int vec) {
+  const char* s = src + (long long)blockIdx.y * src_stride;
+  char* d = dst + (long long)blockIdx.y * dst_stride;
+  const long long n = n_bytes / vec;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  if (vec == 16) {
+    for (long long i = i0; i < n; i += step)
+      reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(s)[i];
+  } else {
+    for (long long i = i0; i < n; i += step)
+      reinterpret_cast<uint32_t*>(d)[i] = reinterpret_cast<const uint32_t*>(s)[i];
+  }
+}
+
+// rows are `row_bytes` wide; segment b starts at base + b*clip_stride + row0*row_bytes
+cudaError_t launch_copy_rows(const void* src, long long src_clip_stride, long long src_row0,
+                             void* dst, long long dst_clip_stride, long long dst_row0,
+                             long long n_rows, int row_bytes, int B, cudaStream_t s) {
+  if (n_rows <= 0 || B <= 0) return cudaSuccess;
+  const char* sp = (const char*)src + src_row0 * row_bytes;
+  char* dp = (char*)dst + dst_row0 * row_bytes;
+  const long long n_bytes = n_rows * row_bytes;
+  const bool a16 = (((uintptr_t)sp | (uintptr_t)dp | (uintptr_t)src_clip_stride | (uintptr_t)dst_clip_stride |
+                     (uintptr_t)n_bytes) & 15) == 0;
+  const int vec = a16 ? 16 : 4;
+  const long long n = n_bytes / vec;
+  int gx = (int)((n + 255) / 256);
+  if (gx > 1024) gx = 1024;
+  if (gx < 1) gx = 1;
+  copy_segments_kernel<<<dim3(gx, B), 256, 0, s>>>(sp, src_clip_stride, dp, dst_clip_stride, n_bytes, vec);
+  return cudaGetLastError();
+}
+
+}  // namespace nasr

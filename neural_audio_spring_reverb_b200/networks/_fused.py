@@ -1,0 +1,220 @@
+"""Host side shared by TCN and GCN: packs the module's parameters into the
+weight blob of the C ABI, owns the nasr_engine handle and routes forward /
+streaming calls to it."""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import torch
+from torch import Tensor
+
+from .. import _native
+
+
+def _path_from_env() -> int:
+    v = os.environ.get("NASR_PATH", "auto").lower()
+    if v in ("auto", "0", ""):
+        return _native.PATH_AUTO
+    if v in ("fp32", "ffma", "1"):
+        return _native.PATH_FP32
+    raise ValueError(f"NASR_PATH={v!r}: expected 'auto' or 'fp32'")
+
+
+class FusedNetMixin:
+    """Expects: self.blocks, self.out_net, self.in_ch, self.out_ch, self.kernel_size,
+    self.cond_dim, self.channels, self.dilations and the class attributes below."""
+
+    _nasr_arch: int = _native.ARCH_TCN
+    _nasr_final_tanh: bool = False
+
+    # ---- construction shared by TCN and GCN -------------------------------
+    def _nasr_build(self, block_cls, n_blocks: int, n_channels: int, dilation_growth: int,
+                    in_ch: int, out_ch: int, kernel_size: int, cond_dim: int) -> None:
+        """Attributes and sub-module names of the reference networks (tcn.py:105-148,
+        gcn.py:91-138): channels, dilations = growth**i, strides, blocks, out_net."""
+        import torch.nn as nn
+
+        self.in_ch, self.out_ch = in_ch, out_ch
+        self.kernel_size, self.cond_dim = kernel_size, cond_dim
+        self.channels = [n_channels] * n_blocks
+        self.dilations = [dilation_growth**i for i in range(n_blocks)]
+        self.n_blocks = n_blocks
+        self.strides = [1] * n_blocks
+        widths = [in_ch] + self.channels
+        self.blocks = nn.ModuleList(
+            block_cls(widths[i], widths[i + 1], kernel_size, self.dilations[i], 1, cond_dim)
+            for i in range(n_blocks))
+        self.out_net = nn.Conv1d(self.channels[-1], out_ch, kernel_size=(1,), stride=(1,), bias=False)
+
+    def calc_receptive_field(self) -> int:
+        """Receptive field in samples (tcn.py:157-164, gcn.py:149-160)."""
+        assert all(s == 1 for s in self.strides)
+        assert self.dilations[0] == 1
+        return self.kernel_size + (self.kernel_size - 1) * sum(self.dilations[1:])
+
+    # ---- engine life cycle -------------------------------------------------
+    def _nasr_has_film(self) -> bool:
+        return hasattr(self.blocks[0], "film")
+
+    def _nasr_tensors(self) -> List[Tensor]:
+        """Parameters/buffers in the order nasr_weight_count() documents."""
+        out: List[Tensor] = []
+        film = self._nasr_has_film()
+        for blk in self.blocks:
+            out += [blk.conv.conv.weight, blk.conv.conv.bias]
+            if film:
+                out += [blk.film.adaptor.weight, blk.film.adaptor.bias, blk.film.bn.weight,
+                        blk.film.bn.bias, blk.film.bn.running_mean, blk.film.bn.running_var]
+            if self._nasr_arch == _native.ARCH_TCN:
+                out.append(blk.act.weight)
+            out.append(blk.res.weight)
+        out.append(self.out_net.weight)
+        return out
+
+    def _nasr_key(self, tensors):
+        return tuple((t.data_ptr(), t._version) for t in tensors)
+
+    def weight_blob(self) -> torch.Tensor:
+        """Flat fp32 CPU tensor: what nasr_engine_create consumes (and what a
+        multi-GPU launch broadcasts once over NCCL)."""
+        return torch.cat([t.detach().reshape(-1).to(device="cpu", dtype=torch.float32)
+                          for t in self._nasr_tensors()])
+
+    def load_weight_blob(self, blob: Tensor) -> None:
+        """Inverse of weight_blob(): fill the parameters/buffers from a flat fp32 tensor
+        (what the other ranks do after the one-time NCCL broadcast)."""
+        tensors = self._nasr_tensors()
+        need = sum(t.numel() for t in tensors)
+        if blob.numel() != need:
+            raise ValueError(f"weight blob has {blob.numel()} floats, expected {need}")
+        off = 0
+        with torch.no_grad():
+            for t in tensors:
+                n = t.numel()
+                t.copy_(blob[off:off + n].reshape(t.shape).to(device=t.device, dtype=t.dtype))
+                off += n
+
+    def _engine(self) -> "_native.Engine":
+        tensors = self._nasr_tensors()
+        dev = tensors[0].device
+        if dev.type != "cuda":
+            raise RuntimeError(
+                f"{type(self).__name__}: parameters are on {dev}; the forward runs only on a B200 "
+                "through libnasr_b200 (no CPU fallback) - move the model with .to('cuda:N')")
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(),
+               self._nasr_key(tensors))
+        eng = self.__dict__.get("_nasr_engine")
+        if eng is None or self.__dict__.get("_nasr_engine_key") != key:
+            if eng is not None:
+                eng.close()
+            blob = self.weight_blob().numpy()
+            eng = _native.Engine(
+                arch=self._nasr_arch, n_blocks=self.n_blocks, in_ch=self.in_ch, out_ch=self.out_ch,
+                n_channels=self.channels[0], kernel_size=self.kernel_size, cond_dim=self.cond_dim,
+                has_film=self._nasr_has_film(), final_tanh=self._nasr_final_tanh,
+                dilations=self.dilations, weights=blob, device=key[0], path=_path_from_env(),
+                bn_eps=float(self.blocks[0].film.bn.eps) if self._nasr_has_film() else 1e-5)
+            self.__dict__["_nasr_engine"] = eng
+            self.__dict__["_nasr_engine_key"] = key
+            self.__dict__["_nasr_stream_B"] = None
+        return eng
+
+    def release_engine(self) -> None:
+        eng = self.__dict__.pop("_nasr_engine", None)
+        if eng is not None:
+            eng.close()
+        self.__dict__.pop("_nasr_engine_key", None)
+
+    # ---- argument checks shared by forward / forward_chunk -----------------
+    def _nasr_check(self, x: Tensor, cond: Optional[Tensor]):
+        assert x.ndim == 3  # (batch_size, in_ch, samples) - tcn.py:151
+        if self.training:
+            raise RuntimeError(f"{type(self).__name__} is inference-only here: call .eval() "
+                               "(training / backward are out of scope of the B200 engine)")
+        if x.shape[1] != self.in_ch:
+            raise ValueError(f"expected {self.in_ch} input channels, got {x.shape[1]}")
+        B = x.shape[0]
+        if self._nasr_has_film() and self.cond_dim > 0:
+            if cond is None:
+                raise ValueError("cond is required when cond_dim > 0")
+            if cond.ndim != 2 or cond.shape[0] != B or cond.shape[1] != self.cond_dim:
+                raise ValueError(f"cond must be [{B}, {self.cond_dim}], got {tuple(cond.shape)}")
+        else:
+            cond = None
+        return B, x.shape[2], cond
+
+    def _nasr_run(self, x: Tensor, cond: Optional[Tensor], chunk: bool) -> Tensor:
+        B, T, cond = self._nasr_check(x, cond)
+        eng = self._engine()
+        dev = torch.device("cuda", eng.device)
+        if x.is_cuda:
+            if x.device != dev:
+                raise RuntimeError(f"input is on {x.device} but the model is on {dev}")
+            xc = x.detach().contiguous().float()
+            y = torch.empty((B, self.out_ch, T), device=dev, dtype=torch.float32)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            cptr = 0
+            if cond is not None:
+                cc = cond.detach().to(device=dev, dtype=torch.float32).contiguous()
+                cptr = cc.data_ptr()
+            eng.set_cond(cptr, B, stream)
+            if T > 0:
+                if chunk:
+                    eng.forward_chunk(xc.data_ptr(), y.data_ptr(), B, T, stream)
+                else:
+                    eng.forward(xc.data_ptr(), y.data_ptr(), B, T, stream)
+            return y
+        # host tensors: the engine copies in, runs, copies out (e2e path of make_inference)
+        xc = x.detach().contiguous().float()
+        cptr = 0
+        if cond is not None:
+            cc = cond.detach().to(device="cpu", dtype=torch.float32).contiguous()
+            cptr = cc.data_ptr()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if chunk:
+            xd = xc.to(dev, non_blocking=True)
+            return self._nasr_run(xd, cond, True).cpu()
+        y = torch.empty((B, self.out_ch, T), dtype=torch.float32, pin_memory=True)
+        eng.forward_host(xc.data_ptr(), cptr, y.data_ptr(), B, T, stream)
+        return y
+
+    # ---- streaming (reference wrapper.py:14-57 semantics) ------------------
+    def reset_stream(self, batch_size: int = 1) -> None:
+        """Zero the per-block input history, like freshly built PaddingCached buffers."""
+        eng = self._engine()
+        dev = torch.device("cuda", eng.device)
+        eng.stream_reset(batch_size, torch.cuda.current_stream(dev).cuda_stream)
+        self.__dict__["_nasr_stream_B"] = batch_size
+
+    def forward_chunk(self, x: Tensor, cond: Optional[Tensor] = None) -> Tensor:
+        """Process the next chunk of a stream; history of the last (k-1)*d input
+        samples of every block is carried across calls."""
+        if self.__dict__.get("_nasr_stream_B") != x.shape[0] or self.__dict__.get("_nasr_engine") is None:
+            self.reset_stream(x.shape[0])
+        return self._nasr_run(x, cond, True)
+
+    def block_forward(self, index: int, x: Tensor, cond: Optional[Tensor] = None) -> Tensor:
+        """One block on its own, x [B, Cin, T] -> [B, C, T] (TCNBlock/GCNBlock.forward)."""
+        if self.training:
+            raise RuntimeError("inference-only: call .eval()")
+        eng = self._engine()
+        dev = torch.device("cuda", eng.device)
+        blk = self.blocks[index]
+        assert x.ndim == 3 and x.shape[1] == blk.in_ch
+        B, _, T = x.shape
+        xc = x.detach().to(dev, torch.float32).contiguous()
+        y = torch.empty((B, blk.out_ch, T), device=dev, dtype=torch.float32)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        cptr = 0
+        if self._nasr_has_film() and self.cond_dim > 0:
+            cc = cond.detach().to(device=dev, dtype=torch.float32).contiguous()
+            cptr = cc.data_ptr()
+        eng.set_cond(cptr, B, stream)
+        if T > 0:
+            eng.block_forward(index, xc.data_ptr(), y.data_ptr(), B, T, stream)
+        return y if x.is_cuda else y.cpu()
+
+    def train(self, mode: bool = True):
+        # nn.Module.train is kept so that .eval() works; forward refuses training mode
+        return super().train(mode)

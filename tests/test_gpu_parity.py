@@ -1,0 +1,194 @@
+"""GPU: the CUDA path (through the Python surface -> C ABI) against the reference's
+golden vectors and against the oracle on seeded inputs. Tolerance: BASELINE.json
+north_star, max|y - y_ref| <= 1e-4 * max|y_ref| per clip, fp32."""
+import pytest
+import torch
+
+from oracle import nasr_oracle as O
+from util import REL_TOL, build_model, golden_inputs, golden_names, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_vectors_from_reference(name):
+    meta, y_ref, sd = load_golden(name)
+    x, cond = golden_inputs(meta)
+    m = build_model(meta["cfg"], sd, DEV)
+    y = m(x.to(DEV), None if cond is None else cond.to(DEV))
+    assert y.shape == y_ref.shape and y.dtype == torch.float32
+    err = rel_err(y, y_ref)
+    assert err <= REL_TOL, f"{name}: {err:.3e}"
+
+
+@pytest.mark.parametrize("name", ["synth_cfg1", "synth_cfg2", "synth_cfg3_c050", "ckpt_TCN_egfxset_20240229_002014_48kHz_cond"])
+def test_host_tensor_path_matches(name):
+    """CPU tensors in -> CPU tensor out through nasr_forward_host (the e2e path)."""
+    meta, y_ref, sd = load_golden(name)
+    x, cond = golden_inputs(meta)
+    m = build_model(meta["cfg"], sd, DEV)
+    y = m(x, cond)
+    assert not y.is_cuda
+    assert rel_err(y, y_ref) <= REL_TOL
+
+
+@pytest.mark.parametrize("cname,B,T", [("cfg1", 3, 48000), ("cfg2", 2, 50000), ("cfg3", 2, 30000),
+                                       ("tcn-shipped", 2, 100001), ("gcn3-shipped", 1, 150003)])
+def test_against_oracle_seeded(cname, B, T):
+    cfg = O.CONFIGS[cname]
+    sd = O.config_state(cname, seed=11)
+    x = O.make_input(B, 1, T, first_clip=5)
+    cond = torch.linspace(0.0, 1.0, B * 2).view(B, 2)
+    m = build_model(cfg, sd, DEV)
+    y = m(x.to(DEV), cond.to(DEV))
+    ref = O.forward(sd, O.config_dilations(cfg), x, cond)
+    assert rel_err(y, ref) <= REL_TOL
+
+
+@pytest.mark.parametrize("T", [1, 2, 31, 127, 128, 129, 1000])
+def test_ragged_and_tiny_lengths(T):
+    cfg = O.CONFIGS["cfg1"]
+    sd = O.config_state("cfg1")
+    x = O.make_input(2, 1, T)
+    cond = torch.tensor([[0.2, 0.4], [0.9, 0.1]])
+    m = build_model(cfg, sd, DEV)
+    y = m(x.to(DEV), cond.to(DEV))
+    ref = O.forward(sd, O.config_dilations(cfg), x, cond)
+    assert y.shape == ref.shape
+    assert float((y.cpu() - ref).abs().max()) <= 1e-4 * max(float(ref.abs().max()), 1e-3)
+
+
+def test_empty_time_axis():
+    m = build_model(O.CONFIGS["cfg1"], O.config_state("cfg1"), DEV)
+    y = m(torch.zeros(2, 1, 0, device=DEV), torch.zeros(2, 2, device=DEV))
+    assert tuple(y.shape) == (2, 1, 0)
+
+
+def test_causality():
+    """output[:t] does not depend on input[t:]"""
+    cfg = O.CONFIGS["cfg2"]
+    m = build_model(cfg, O.config_state("cfg2"), DEV)
+    x = O.make_input(1, 1, 30000).to(DEV)
+    cond = torch.tensor([[0.5, 0.5]], device=DEV)
+    y1 = m(x, cond)
+    x2 = x.clone()
+    x2[..., 17000:] = torch.randn_like(x2[..., 17000:])
+    y2 = m(x2, cond)
+    assert torch.equal(y1[..., :17000], y2[..., :17000])
+    assert not torch.equal(y1[..., 17000:], y2[..., 17000:])
+
+
+def test_batch_shard_invariance():
+    """clips are independent: any split of the batch gives the same rows (multi-GPU sharding relies on it)"""
+    cfg = O.CONFIGS["cfg2"]
+    m = build_model(cfg, O.config_state("cfg2"), DEV)
+    x = O.make_input(5, 1, 20000).to(DEV)
+    cond = torch.rand(5, 2, device=DEV)
+    full = m(x, cond)
+    parts = torch.cat([m(x[:2], cond[:2]), m(x[2:], cond[2:])])
+    assert torch.equal(full, parts)
+
+
+@pytest.mark.parametrize("cname,chunk", [("cfg1", 1024), ("cfg2", 1024), ("cfg2", 65536), ("cfg2", 777),
+                                         ("cfg3", 4096), ("gcn3-shipped", 65536), ("tcn-shipped", 1024)])
+def test_streaming_equals_oneshot(cname, chunk):
+    """Carried per-block history (wrapper.py:14-57): chunked == one-shot."""
+    import neural_audio_spring_reverb_b200 as N
+    cfg = O.CONFIGS[cname]
+    m = build_model(cfg, O.config_state(cname), DEV)
+    T = 200000 if cname == "gcn3-shipped" else (100000 if cname == "tcn-shipped" else 40000)
+    x = O.make_input(2, 1, T).to(DEV)
+    cond = torch.tensor([[0.5, 0.5], [0.0, 1.0]], device=DEV)
+    one = m(x, cond)
+    st = N.CachedStream(m)
+    outs = [st(x[..., s:s + chunk], cond) for s in range(0, T, chunk)]
+    got = torch.cat(outs, -1)
+    assert rel_err(got, one) <= 1e-6
+    st.reset(2)  # reset gives zero history again
+    again = st(x[..., :chunk], cond)
+    assert rel_err(again, one[..., :chunk]) <= 1e-6
+
+
+def test_streaming_against_oracle_cached_padding():
+    cfg = O.CONFIGS["cfg1"]
+    sd = O.config_state("cfg1")
+    m = build_model(cfg, sd, DEV)
+    x = O.make_input(2, 1, 5000)
+    cond = torch.tensor([[0.3, 0.3], [0.6, 0.2]])
+    state = O.StreamState(sd, O.config_dilations(cfg), 2)
+    m.reset_stream(2)
+    for s in range(0, 5000, 1024):
+        ref = O.forward_chunk(sd, O.config_dilations(cfg), state, x[..., s:s + 1024], cond)
+        got = m.forward_chunk(x[..., s:s + 1024].to(DEV), cond.to(DEV))
+        assert rel_err(got, ref) <= REL_TOL
+
+
+@pytest.mark.parametrize("cname", ["cfg1", "cfg3"])
+def test_single_block_forward(cname):
+    """TCNBlock / GCNBlock.forward through nasr_block_forward, incl. impulse response."""
+    cfg = O.CONFIGS[cname]
+    sd = O.config_state(cname)
+    dil = O.config_dilations(cfg)
+    m = build_model(cfg, sd, DEV)
+    cond = torch.tensor([[0.5, 0.25]])
+    for i in (0, 1, cfg["n_blocks"] - 1):
+        cin = 1 if i == 0 else cfg["n_channels"]
+        x = torch.zeros(1, cin, 3000)
+        x[0, :, 100] = 1.0                      # impulse
+        x[0, :, 1500:] = O.make_input(1, cin, 1500)[0]
+        y = m.block_forward(i, x.to(DEV), cond.to(DEV))
+        ref = O.block_forward(sd, i, dil[i], x, cond)
+        assert rel_err(y, ref) <= REL_TOL
+
+
+def test_cond_changes_output_and_reference_default():
+    meta, y_ref, sd = load_golden("ckpt_GCN_3_egfxset_20240324_160003_48kHz_cond")
+    x, cond = golden_inputs(meta)
+    m = build_model(meta["cfg"], sd, DEV)
+    y = m(x.to(DEV), cond.to(DEV))
+    y0 = m(x.to(DEV), torch.zeros_like(cond).to(DEV))
+    assert rel_err(y, y_ref) <= REL_TOL
+    assert rel_err(y0, y_ref) > 1e-3
+
+
+def test_errors():
+    cfg = O.CONFIGS["cfg1"]
+    m = build_model(cfg, O.config_state("cfg1"), DEV)
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 100, device=DEV), torch.zeros(1, 2, device=DEV))      # tcn.py:151
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 1, 100, device=DEV), None)
+    m.train()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 100, device=DEV), torch.zeros(1, 2, device=DEV))
+    m.eval()
+
+
+def test_make_inference_and_rtf_plumbing(tmp_path):
+    """inference.py:12-91 / rtf.py:24-33 with a checkpoint in the reference's format."""
+    import types
+    import neural_audio_spring_reverb_b200 as N
+    meta, _, sd = load_golden("ckpt_TCN_egfxset_20240229_002014_48kHz")
+    c = meta["cfg"]
+    config = dict(name="TCN", model_type="TCN", cond_dim=2, c0=0.0, c1=0.0, in_ch=1, out_ch=1, n_channels=c["n_channels"],
+                  n_layers=c["n_blocks"], dilation_growth=c["dilation_growth"], kernel_size=c["kernel_size"],
+                  sample_rate=48000, batch_size=16)
+    ck = tmp_path / "tcn.pt"
+    torch.save({"label": "t", "timestamp": "0", "model_state_dict": sd, "optimizer_state_dict": {},
+                "scheduler_state_dict": {}, "config_state_dict": config}, ck)
+    args = types.SimpleNamespace(checkpoint=str(ck), device=torch.device(DEV), audio_dir=str(tmp_path),
+                                 input=O.make_input(1, 1, 48000)[0].numpy())
+    pred = N.make_inference(args)
+    assert tuple(pred.shape) == (1, 48000) and abs(float(pred.abs().max()) - 1.0) < 1e-6
+    # the same plumbing on the oracle: 16 rows x 3000 samples, normalise, 20 Hz high-pass, normalise
+    import torchaudio
+    x = torch.as_tensor(args.input).reshape(16, 1, -1)
+    ref = O.forward(sd, meta["dilations"], x, torch.zeros(16, 2))
+    ref = ref / ref.abs().max()
+    ref = torchaudio.functional.highpass_biquad(ref, 48000, 20).reshape(1, -1)
+    ref = ref / ref.abs().max()
+    assert rel_err(pred, ref) <= REL_TOL
+    from neural_audio_spring_reverb_b200.rtf import measure_rtf
+    out = measure_rtf(types.SimpleNamespace(checkpoint=str(ck), device=torch.device(DEV), audio_dir=str(tmp_path)))
+    assert tuple(out.shape) == (1, 48000)

@@ -1,0 +1,75 @@
+"""CPU: the oracle restatement against the golden vectors produced by the reference."""
+import pytest
+import torch
+
+from oracle import nasr_oracle as O
+from util import golden_inputs, golden_names, load_golden, rel_err
+
+# long fixtures are covered by the GPU parity test; keep the CPU suite to a few minutes
+CPU_CASES = [n for n in golden_names() if not n.startswith("ckpt_GCN_99_egfxset_20240310_095201_48kHz.")]
+
+
+@pytest.mark.parametrize("name", CPU_CASES)
+def test_oracle_matches_reference_golden(name):
+    meta, y_ref, sd = load_golden(name)
+    x, cond = golden_inputs(meta)
+    torch.set_num_threads(8)
+    y = O.forward(sd, meta["dilations"], x, cond)
+    # same ATen operators as the reference -> agreement at the fp32 noise floor
+    assert y.shape == y_ref.shape
+    assert rel_err(y, y_ref) <= 2e-6, rel_err(y, y_ref)
+
+
+@pytest.mark.parametrize("name", ["synth_cfg1", "synth_tcn_io2", "synth_gcn_c6"])
+def test_oracle_fp64_is_within_reference_noise(name):
+    meta, y_ref, sd = load_golden(name)
+    x, cond = golden_inputs(meta)
+    y64 = O.forward(sd, meta["dilations"], x, cond, dtype=torch.float64)
+    assert rel_err(y64, y_ref) <= 1e-5
+
+
+@pytest.mark.parametrize("name,chunk", [("synth_cfg1", 1024), ("synth_cfg1", 37), ("synth_gcn_c6", 300)])
+def test_oracle_streaming_equals_oneshot(name, chunk):
+    """wrapper.py's cached padding: chunked == one-shot (bit-exact in the reference)."""
+    meta, y_ref, sd = load_golden(name)
+    x, cond = golden_inputs(meta)
+    st = O.StreamState(sd, meta["dilations"], meta["B"])
+    outs = [O.forward_chunk(sd, meta["dilations"], st, x[..., s:s + chunk], cond) for s in range(0, meta["T"], chunk)]
+    assert rel_err(torch.cat(outs, -1), y_ref) <= 2e-6
+
+
+def test_known_answers_from_reference_logs():
+    """logs/model_report.txt:68,98,148,179 - parameter counts and receptive fields."""
+    meta, _, sd = load_golden("ckpt_TCN_egfxset_20240229_002014_48kHz")
+    assert meta["params"] == 17989 and meta["rf"] == 82743
+    assert O.receptive_field(3, meta["dilations"]) == 82743
+    meta, _, sd = load_golden("ckpt_GCN_3_egfxset_20240324_160003_48kHz_cond")
+    assert meta["params"] == 61312 and meta["rf"] == 131587
+    assert O.receptive_field(3, meta["dilations"]) == 131587
+
+
+def test_impulse_response_of_one_block_is_the_kernel():
+    """A single TCN block without FiLM fed a unit impulse returns PReLU(w[:, 0, ::-1 taps] + b) + res."""
+    sd = O.build_state("TCN", 1, 4, 5, 0, seed=3)
+    x = torch.zeros(1, 1, 64)
+    x[0, 0, 10] = 1.0
+    y = O.block_forward(sd, 0, 3, x, None)
+    w = sd["blocks.0.conv.conv.weight"][:, 0]          # [C, k]
+    b = sd["blocks.0.conv.conv.bias"]
+    a = sd["blocks.0.act.weight"]
+    for j in range(5):
+        t = 10 + (4 - j) * 3
+        pre = w[:, j] + b
+        exp = torch.where(pre > 0, pre, a * pre) + (sd["blocks.0.res.weight"][:, 0, 0] if t == 10 else 0)
+        assert torch.allclose(y[0, :, t], exp, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["synth_cfg1", "synth_tcn_nofilm", "synth_tcn_io2", "synth_gcn_c6"])
+def test_c_oracle_matches_reference_golden(name):
+    """The independent plain-C restatement (fp64 accumulation) against the reference's output."""
+    from oracle import c_oracle
+    meta, y_ref, sd = load_golden(name)
+    x, cond = golden_inputs(meta)
+    T = min(meta["T"], 1500)
+    y = c_oracle.forward(sd, meta["dilations"], x[..., :T].contiguous(), cond)
+    assert rel_err(y, y_ref[..., :T]) <= 1e-5
