@@ -3,6 +3,7 @@
 // streaming history; enqueues one fused block kernel per network block.
 #include "../../include/nasr_b200.h"
 #include "common.cuh"
+#include "tc_block.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -29,8 +30,10 @@ struct BlockState {
   long long hist = 0;  // (k-1)*d rows of input history (custom_layers.py:71-73)
   float *wconv = nullptr, *wres = nullptr;
   float *bias = nullptr, *adw = nullptr, *adb = nullptr, *bnw = nullptr, *bnb = nullptr, *mean = nullptr, *var = nullptr;
-  int* perm = nullptr;
+  int* perm = nullptr;                        // conv channel -> index in scale/shift ([tanh | sigmoid] halves padded)
   float *scale = nullptr, *shift = nullptr;  // [condCap][Wp]
+  uint16_t* wtc = nullptr;                   // tcgen05 path: split-fp16 weight tiles (tc_pack_weights)
+  float inv_sw = 1.f, inv_sr = 1.f;
 };
 
 }  // namespace
@@ -153,6 +156,8 @@ void free_block(BlockState& b) {
   }
   if (b.perm) cudaFree(b.perm);
   b.perm = nullptr;
+  if (b.wtc) cudaFree(b.wtc);
+  b.wtc = nullptr;
 }
 
 BlockArgs make_args(const nasr_engine* e, int i, int B) {
@@ -169,8 +174,22 @@ BlockArgs make_args(const nasr_engine* e, int i, int B) {
   return a;
 }
 
-int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s) {
-  cudaError_t err = launch_generic_block(a, e->sm_count, s);
+int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool allow_tc = true) {
+  const BlockState& bs = e->blocks[i];
+  cudaError_t err;
+  if (allow_tc && bs.path == 1) {
+    TcLaunch L{};
+    L.in = a.in; L.in_rows = a.in_rows; L.in_clip_stride_elems = a.in_clip_stride;
+    L.wpacked = bs.wtc; L.arch = e->desc.arch; L.sm_count = e->sm_count;
+    TcArgs& t = L.a;
+    t.out = a.out; t.out_fmt = a.out_fmt; t.out_clip_stride = a.out_clip_stride; t.out_rows = a.out_rows;
+    t.out_row0 = a.out_row0; t.in_row0 = a.in_row0; t.B = a.B; t.T = a.T; t.k = a.k; t.d = a.d;
+    t.scale = a.scale; t.shift = a.shift; t.slope = a.slope; t.inv_sw = bs.inv_sw; t.inv_sr = bs.inv_sr;
+    t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh;
+    err = launch_tc_block(L, s);
+  } else {
+    err = launch_generic_block(a, e->sm_count, s);
+  }
   if (err != cudaSuccess)
     return fail(e, err == cudaErrorInvalidConfiguration ? NASR_ERR_INVALID : NASR_ERR_CUDA,
                 "block " + std::to_string(i) + " launch: " + cudaGetErrorString(err));
@@ -267,22 +286,27 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
     b.k = k; b.d = desc->dilations[i];
     b.hist = (long long)(k - 1) * b.d;
     b.NC = pick_nc(desc->arch, Cp);
-    b.path = 0;
-    b.in_fmt = (i == 0) ? FMT_NCT : FMT_CL;
-    b.out_fmt = (i == n - 1) ? FMT_FINAL : FMT_CL;
+    const bool want_tc = desc->path == NASR_PATH_AUTO;
+    auto is_tc = [&](int blk) { return want_tc && blk >= 1 && blk < n && tc_eligible(desc->arch, C, C, k); };
+    b.path = is_tc(i) ? 1 : 0;
+    b.in_fmt = (i == 0) ? FMT_NCT : (b.path == 1 ? FMT_SPLIT16 : FMT_CL);
+    b.out_fmt = (i == n - 1) ? FMT_FINAL : (is_tc(i + 1) ? FMT_SPLIT16 : FMT_CL);
     if (b.Wp / b.NC > 16) { rc = fail(nullptr, NASR_ERR_INVALID, "channel count too large for the generic kernel"); break; }
 
-    // permutation: original conv channel -> packed column (GCN: tanh/sigmoid halves
-    // of the same output channel group land in one thread, custom_layers.py:103-111)
-    std::vector<int> perm(b.W);
+    // packed column of each conv channel in the generic kernel's weight tiles (GCN: the tanh and
+    // sigmoid halves of one output-channel group sit in one thread, custom_layers.py:103-111),
+    // and its index in the scale/shift vectors (original order, halves padded to Cp)
+    std::vector<int> col(b.W), perm(b.W);
     if (!gcn) {
-      for (int c = 0; c < b.W; ++c) perm[c] = c;
+      for (int c = 0; c < b.W; ++c) col[c] = perm[c] = c;
     } else {
       const int h = b.NC / 2;
       for (int c = 0; c < C; ++c) {
         const int g = c / h, j = c % h;
-        perm[c] = g * b.NC + j;
-        perm[C + c] = g * b.NC + h + j;
+        col[c] = g * b.NC + j;
+        col[C + c] = g * b.NC + h + j;
+        perm[c] = c;
+        perm[C + c] = Cp + c;
       }
     }
     const float* conv_w = p; p += (size_t)b.W * b.Cin * k;
@@ -304,12 +328,17 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
     for (int co = 0; co < b.W; ++co)
       for (int ci = 0; ci < b.Cin; ++ci)
         for (int j = 0; j < k; ++j)
-          h_wconv[((size_t)j * b.Cinp + ci) * b.Wp + perm[co]] = conv_w[((size_t)co * b.Cin + ci) * k + j];
+          h_wconv[((size_t)j * b.Cinp + ci) * b.Wp + col[co]] = conv_w[((size_t)co * b.Cin + ci) * k + j];
     std::vector<float> h_wres((size_t)b.Cinp * b.Coutp, 0.f);
     for (int co = 0; co < C; ++co)
       for (int ci = 0; ci < b.Cin; ++ci) h_wres[(size_t)ci * b.Coutp + co] = res_w[(size_t)co * b.Cin + ci];
 
     up(&b.wconv, h_wconv); up(&b.wres, h_wres); up(&b.bias, h_bias); up(&b.perm, perm);
+    if (b.path == 1) {
+      std::vector<uint16_t> h_wtc;
+      tc_pack_weights(desc->arch, k, conv_w, res_w, h_wtc, &b.inv_sw, &b.inv_sr);
+      up(&b.wtc, h_wtc);
+    }
     if (desc->has_film) {
       if (h_adw.empty()) h_adw.push_back(0.f);  // cond_dim == 0: Linear(0, 2W) is bias only
       up(&b.adw, h_adw); up(&b.adb, h_adb); up(&b.bnw, h_bnw); up(&b.bnb, h_bnb); up(&b.mean, h_mean); up(&b.var, h_var);
@@ -668,7 +697,7 @@ int nasr_block_forward(nasr_engine* e, int block, const float* x_dev, float* y_d
   a.in_fmt = FMT_NCT; a.out_fmt = FMT_NCT;
   a.in = x_dev; a.in_clip_stride = (long long)bs.Cin * T; a.in_rows = T; a.in_row0 = 0;
   a.out = y_dev; a.out_clip_stride = (long long)bs.Cout * T; a.out_rows = T; a.out_row0 = 0;
-  return launch_block(e, a, block, (cudaStream_t)stream);
+  return launch_block(e, a, block, (cudaStream_t)stream, /*allow_tc=*/false);
 }
 
 size_t nasr_workspace_bytes(const nasr_engine* e, int B, int64_t T) {

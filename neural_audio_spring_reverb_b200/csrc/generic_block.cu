@@ -21,7 +21,6 @@
 // feeds 16-32 FFMAs.
 #include "common.cuh"
 #include <cuda_fp16.h>
-#include <cuda_bf16.h>
 
 namespace nasr {
 
@@ -98,7 +97,7 @@ __global__ void __launch_bounds__(512, 1) generic_block_kernel(const BlockArgs a
         const float* g = ok ? src + (long long)(c0 + ci) * a.in_rows + row : src;
         cp_async4(xs + r * XS + ci, g, ok);
       }
-    } else {  // FMT_SPLIT16: value = fp16 hi + bf16 lo
+    } else {  // FMT_SPLIT16: value = fp16 hi + fp16 lo
       const __half* src = (const __half*)a.in + (long long)b * a.in_clip_stride;
       for (int i = threadIdx.x; i < TM * CK; i += nthreads) {
         const int r = i / CK, ci = i - r * CK;
@@ -107,7 +106,7 @@ __global__ void __launch_bounds__(512, 1) generic_block_kernel(const BlockArgs a
         float v = 0.f;
         if (ok) {
           const __half* p = src + row * (2LL * a.Cinp) + c0 + ci;
-          v = __half2float(p[0]) + __bfloat162float(((const __nv_bfloat16*)p)[a.Cinp]);
+          v = __half2float(p[0]) + __half2float(p[a.Cinp]);
         }
         xs[r * XS + ci] = v;
       }
@@ -236,11 +235,14 @@ __global__ void __launch_bounds__(512, 1) generic_block_kernel(const BlockArgs a
       const long long tile = blockIdx.x + tl * gridDim.x;
       const int b = (int)(tile / tiles_per_clip);
       const long long t0 = (tile - (long long)b * tiles_per_clip) * TM;
+      // scale/shift are stored in original channel order ([tanh | sigmoid] halves for GCN,
+      // each padded to Coutp); this thread's packed columns map to ro0.. and Coutp + ro0..
       float sc[NC], sh[NC];
 #pragma unroll
       for (int n = 0; n < NC; n += 4) {
-        const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.scale + (long long)b * Wp + co0 + n));
-        const float4 h4 = __ldg(reinterpret_cast<const float4*>(a.shift + (long long)b * Wp + co0 + n));
+        const int idx = (ARCH == 1 && n >= NCO) ? (Coutp + ro0 + n - NCO) : ((ARCH == 1 ? ro0 : co0) + n);
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.scale + (long long)b * Wp + idx));
+        const float4 h4 = __ldg(reinterpret_cast<const float4*>(a.shift + (long long)b * Wp + idx));
         sc[n] = s4.x; sc[n + 1] = s4.y; sc[n + 2] = s4.z; sc[n + 3] = s4.w;
         sh[n] = h4.x; sh[n + 1] = h4.y; sh[n + 2] = h4.z; sh[n + 3] = h4.w;
       }
@@ -275,15 +277,16 @@ __global__ void __launch_bounds__(512, 1) generic_block_kernel(const BlockArgs a
         } else if (a.out_fmt == FMT_SPLIT16) {
           if (ok) {
             __half* dst = (__half*)a.out + (long long)b * a.out_clip_stride + (a.out_row0 + t) * (2LL * Coutp) + ro0;
-            __nv_bfloat16* dlo = (__nv_bfloat16*)dst + Coutp;
+            __half* dlo = dst + Coutp;
             __align__(8) __half hi[4];
-            __align__(8) __nv_bfloat16 lo[4];
+            __align__(8) __half lo[4];
 #pragma unroll
             for (int n = 0; n < NCO; n += 4) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                hi[q] = __float2half_rn(o[n + q]);
-                lo[q] = __float2bfloat16_rn(o[n + q] - __half2float(hi[q]));
+                const float xv = fminf(fmaxf(o[n + q], -65504.f), 65504.f);
+                hi[q] = __float2half_rn(xv);
+                lo[q] = __float2half_rn(xv - __half2float(hi[q]));
               }
               *reinterpret_cast<uint2*>(dst + n) = *reinterpret_cast<const uint2*>(hi);
               *reinterpret_cast<uint2*>(dlo + n) = *reinterpret_cast<const uint2*>(lo);
