@@ -47,6 +47,9 @@ struct BlockArgs {
 };
 
 cudaError_t launch_generic_block(const BlockArgs& a, int sm_count, cudaStream_t s);
+// first block (Cin = in_ch <= 4): w0 = conv weights [k][Cin][W] in original channel order;
+// returns cudaErrorNotSupported outside its envelope
+cudaError_t launch_first_block(const BlockArgs& a, const float* w0, int sm_count, cudaStream_t s);
 
 // fold: scale/shift[b][packed(w)] for one block (custom_layers.py:32-42 folded with conv bias)
 struct FoldArgs {

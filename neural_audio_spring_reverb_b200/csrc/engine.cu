@@ -32,6 +32,7 @@ struct BlockState {
   float *bias = nullptr, *adw = nullptr, *adb = nullptr, *bnw = nullptr, *bnb = nullptr, *mean = nullptr, *var = nullptr;
   int* perm = nullptr;                        // conv channel -> index in scale/shift ([tanh | sigmoid] halves padded)
   float *scale = nullptr, *shift = nullptr;  // [condCap][Wp]
+  float* w0 = nullptr;                       // first block: conv weights [k][Cin][W], original order
   uint16_t* wtc = nullptr;                   // tcgen05 path: split-fp16 weight tiles (tc_pack_weights)
   float inv_sw = 1.f, inv_sr = 1.f;
 };
@@ -158,6 +159,8 @@ void free_block(BlockState& b) {
   b.perm = nullptr;
   if (b.wtc) cudaFree(b.wtc);
   b.wtc = nullptr;
+  if (b.w0) cudaFree(b.w0);
+  b.w0 = nullptr;
 }
 
 BlockArgs make_args(const nasr_engine* e, int i, int B) {
@@ -188,7 +191,9 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
     t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh;
     err = launch_tc_block(L, s);
   } else {
-    err = launch_generic_block(a, e->sm_count, s);
+    err = cudaErrorNotSupported;
+    if (bs.w0 && allow_tc) err = launch_first_block(a, bs.w0, e->sm_count, s);
+    if (err == cudaErrorNotSupported) err = launch_generic_block(a, e->sm_count, s);
   }
   if (err != cudaSuccess)
     return fail(e, err == cudaErrorInvalidConfiguration ? NASR_ERR_INVALID : NASR_ERR_CUDA,
@@ -334,6 +339,13 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
       for (int ci = 0; ci < b.Cin; ++ci) h_wres[(size_t)ci * b.Coutp + co] = res_w[(size_t)co * b.Cin + ci];
 
     up(&b.wconv, h_wconv); up(&b.wres, h_wres); up(&b.bias, h_bias); up(&b.perm, perm);
+    if (i == 0 && b.Cin <= 4) {
+      std::vector<float> h_w0((size_t)k * b.Cin * b.W);
+      for (int co = 0; co < b.W; ++co)
+        for (int ci = 0; ci < b.Cin; ++ci)
+          for (int j = 0; j < k; ++j) h_w0[((size_t)j * b.Cin + ci) * b.W + co] = conv_w[((size_t)co * b.Cin + ci) * k + j];
+      up(&b.w0, h_w0);
+    }
     if (b.path == 1) {
       std::vector<uint16_t> h_wtc;
       tc_pack_weights(desc->arch, k, conv_w, res_w, h_wtc, &b.inv_sw, &b.inv_sr);

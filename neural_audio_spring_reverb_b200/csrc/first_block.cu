@@ -1,0 +1,164 @@
+// First block of the network (Cin = in_ch, usually 1): HBM-bound, so it gets its own
+// kernel instead of the tap-streaming generic one.  One thread owns one output sample
+// and all C (TCN) / 2C (GCN) conv channels in registers; the input window of the CTA
+// and the (tiny) weights live in shared memory.  Same arithmetic as the other block
+// kernels (reference src/nasr/networks/tcn.py:73-86, gcn.py:53-61,
+// custom_layers.py:32-42,85-88); reads 4*Cin bytes and writes one 4*C-byte row per sample.
+#include "common.cuh"
+#include <cuda_fp16.h>
+
+namespace nasr {
+
+constexpr int FB_ROWS = 256;   // samples per CTA tile = threads per CTA
+
+template <int ARCH, int C>
+__global__ void __launch_bounds__(FB_ROWS, 2) first_block_kernel(const BlockArgs a, const float* __restrict__ w0) {
+  constexpr int W = ARCH == 1 ? 2 * C : C;
+  extern __shared__ __align__(16) float fsm[];
+  const int Cin = a.Cin, k = a.k, d = a.d;
+  const int H = (k - 1) * d;
+  float* ws = fsm;                         // [k][Cin][W]   original channel order
+  float* rs = ws + k * Cin * W;            // [Cin][C]
+  float* os = rs + Cin * C;                // [out_ch][C]   (FMT_FINAL)
+  float* xs = os + (a.out_fmt == FMT_FINAL ? a.out_ch * C : 0);   // [Cin][H + FB_ROWS]
+  const int XW = H + FB_ROWS;
+
+  for (int i = threadIdx.x; i < k * Cin * W; i += FB_ROWS) ws[i] = w0[i];
+  for (int i = threadIdx.x; i < Cin * C; i += FB_ROWS) {
+    const int ci = i / C, c = i - ci * C;
+    rs[i] = a.wres[ci * a.Coutp + c];
+  }
+  if (a.out_fmt == FMT_FINAL)
+    for (int i = threadIdx.x; i < a.out_ch * C; i += FB_ROWS) os[i] = a.wout[(i / C) * a.Coutp + (i % C)];
+
+  const long long tiles_per_clip = (a.T + FB_ROWS - 1) / FB_ROWS;
+  const long long ntiles = tiles_per_clip * a.B;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b = (int)(tile / tiles_per_clip);
+    const long long t0 = (tile - (long long)b * tiles_per_clip) * FB_ROWS;
+    __syncthreads();   // previous tile's readers are done (also orders the weight fill)
+    const float* src = (const float*)a.in + (long long)b * a.in_clip_stride;
+    for (int i = threadIdx.x; i < Cin * XW; i += FB_ROWS) {
+      const int ci = i / XW, p = i - ci * XW;
+      const long long t = t0 - H + p, row = a.in_row0 + t;
+      xs[i] = (row >= 0 && t < a.T) ? __ldg(src + (long long)ci * a.in_rows + row) : 0.f;
+    }
+    __syncthreads();
+
+    const int r = threadIdx.x;
+    const long long t = t0 + r;
+    float acc[W];
+#pragma unroll
+    for (int n = 0; n < W; ++n) acc[n] = 0.f;
+    for (int j = 0; j < k; ++j)
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float xv = xs[ci * XW + r + j * d];
+        const float4* wv = reinterpret_cast<const float4*>(ws + (j * Cin + ci) * W);
+#pragma unroll
+        for (int n = 0; n < W / 4; ++n) {
+          const float4 q = wv[n];
+          acc[4 * n] = fmaf(xv, q.x, acc[4 * n]);
+          acc[4 * n + 1] = fmaf(xv, q.y, acc[4 * n + 1]);
+          acc[4 * n + 2] = fmaf(xv, q.z, acc[4 * n + 2]);
+          acc[4 * n + 3] = fmaf(xv, q.w, acc[4 * n + 3]);
+        }
+      }
+    const float* sc = a.scale + (long long)b * a.Wp;
+    const float* sh = a.shift + (long long)b * a.Wp;
+    float o[C];
+    if (ARCH == 0) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float y = fmaf(acc[c], __ldg(sc + c), __ldg(sh + c));
+        o[c] = y > 0.f ? y : a.slope * y;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float yt = fmaf(acc[c], __ldg(sc + c), __ldg(sh + c));
+        const float ys = fmaf(acc[C + c], __ldg(sc + a.Coutp + c), __ldg(sh + a.Coutp + c));
+        o[c] = tanhf(yt) * (1.0f / (1.0f + expf(-ys)));
+      }
+    }
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float xv = xs[ci * XW + r + H];
+#pragma unroll
+      for (int c = 0; c < C; ++c) o[c] = fmaf(xv, rs[ci * C + c], o[c]);
+    }
+    if (t < a.T) {
+      if (a.out_fmt == FMT_SPLIT16) {
+        __half* dst = (__half*)a.out + (long long)b * a.out_clip_stride + (a.out_row0 + t) * (2LL * a.Coutp);
+        uint32_t hi[C / 2], lo[C / 2];
+#pragma unroll
+        for (int c = 0; c < C; c += 2) {
+          const float x0 = fminf(fmaxf(o[c], -65504.f), 65504.f), x1 = fminf(fmaxf(o[c + 1], -65504.f), 65504.f);
+          const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+          const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+          hi[c >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          lo[c >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        uint4* l4 = reinterpret_cast<uint4*>(dst + a.Coutp);
+#pragma unroll
+        for (int v = 0; v < C / 8; ++v) {
+          d4[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+          l4[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+        }
+      } else if (a.out_fmt == FMT_CL) {
+        float4* dst = reinterpret_cast<float4*>((float*)a.out + (long long)b * a.out_clip_stride +
+                                                (a.out_row0 + t) * (long long)a.Coutp);
+#pragma unroll
+        for (int v = 0; v < C / 4; ++v) dst[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+      } else {  // FMT_FINAL
+        for (int oc = 0; oc < a.out_ch; ++oc) {
+          float y = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) y = fmaf(o[c], os[oc * C + c], y);
+          if (a.final_tanh) y = tanhf(y);
+          ((float*)a.out)[(long long)b * a.out_clip_stride + (long long)oc * a.out_rows + a.out_row0 + t] = y;
+        }
+      }
+    }
+  }
+}
+
+template <int ARCH, int C>
+static cudaError_t launch_fb(const BlockArgs& a, const float* w0, int sm_count, cudaStream_t s) {
+  constexpr int W = ARCH == 1 ? 2 * C : C;
+  const int H = (a.k - 1) * a.d;
+  const size_t smem = sizeof(float) * ((size_t)a.k * a.Cin * W + (size_t)a.Cin * C +
+                                       (a.out_fmt == FMT_FINAL ? (size_t)a.out_ch * C : 0) + (size_t)a.Cin * (H + FB_ROWS));
+  if (smem > 100 * 1024) return cudaErrorNotSupported;
+  auto kern = first_block_kernel<ARCH, C>;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    configured = smem;
+  }
+  const long long ntiles = ((a.T + FB_ROWS - 1) / FB_ROWS) * a.B;
+  long long grid = (long long)sm_count * 4;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<(unsigned)grid, FB_ROWS, smem, s>>>(a, w0);
+  return cudaGetLastError();
+}
+
+// w0: conv weights [k][Cin][W] fp32 in original channel order. Returns cudaErrorNotSupported
+// when the shape is outside this kernel's envelope (the caller falls back to the generic kernel).
+cudaError_t launch_first_block(const BlockArgs& a, const float* w0, int sm_count, cudaStream_t s) {
+  if (a.in_fmt != FMT_NCT || a.Cin > 4 || a.Cout != a.Coutp) return cudaErrorNotSupported;
+  if (a.out_fmt != FMT_SPLIT16 && a.out_fmt != FMT_CL && a.out_fmt != FMT_FINAL) return cudaErrorNotSupported;
+  if ((long long)(a.k - 1) * a.d > 8192) return cudaErrorNotSupported;
+  if (a.B <= 0 || a.T <= 0) return cudaSuccess;
+  if (a.arch == 0) {
+    if (a.Cout == 16) return launch_fb<0, 16>(a, w0, sm_count, s);
+    if (a.Cout == 32) return launch_fb<0, 32>(a, w0, sm_count, s);
+    if (a.Cout == 64) return launch_fb<0, 64>(a, w0, sm_count, s);
+  } else {
+    if (a.Cout == 16) return launch_fb<1, 16>(a, w0, sm_count, s);
+    if (a.Cout == 32) return launch_fb<1, 32>(a, w0, sm_count, s);
+  }
+  return cudaErrorNotSupported;
+}
+
+}  // namespace nasr

@@ -117,6 +117,10 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
+__host__ __device__ constexpr uint32_t make_desc_sw128_hi() {
+  return (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
+}
+
 enum : uint32_t { FMT_F16 = 0, FMT_BF16 = 1, FMT_TF32 = 2 };
 
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, both operands K-major.
@@ -151,6 +155,25 @@ __device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
       :
       : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+// K-major SWIZZLE_128B descriptor high word: SBO = 1024 B, version 1, layout type 2
+#define NASR_DESC_HI_SW128 0x40004040
+// Variant with the descriptor high word and the instruction descriptor as immediates (they
+// then live in uniform registers for free) and a per-lane predicate: exactly one lane of the
+// (converged) warp passes pred != 0 and its a_lo / b_lo / tmem_d / accumulate are used.
+template <uint32_t IDESC>
+__device__ __forceinline__ void umma_f16_imm(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate,
+                                             uint32_t pred) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "setp.ne.b32 q, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(accumulate), "r"(pred), "n"(NASR_DESC_HI_SW128), "n"(IDESC)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_if(uint64_t* bar, uint32_t leader) {

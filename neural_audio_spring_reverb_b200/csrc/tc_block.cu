@@ -48,6 +48,22 @@ __device__ __forceinline__ long long floordiv(long long a, long long b) {
   return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
 }
 
+// issuer side: wait until all four epilogue warps have drained at least `need` tiles
+__device__ __forceinline__ void wait_drained(volatile uint32_t* epi_done, int need) {
+  if (need <= 0) return;
+  const uint32_t addr = sm100::smem_u32((const void*)epi_done);
+  while (true) {
+    uint32_t d0, d1, d2, d3;
+    asm volatile("ld.acquire.cta.shared::cta.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3)
+                 : "r"(addr)
+                 : "memory");
+    const uint32_t m01 = d0 < d1 ? d0 : d1, m23 = d2 < d3 ? d2 : d3;
+    if ((int)(m01 < m23 ? m01 : m23) >= need) break;
+  }
+  sm100::tc_fence_after();
+}
+
 // per-CTA walk over groups of up to G tiles of one strip (same clip, same lane)
 struct Sched {
   long long idx, idx_end;
@@ -83,8 +99,11 @@ struct Sched {
   }
 };
 
+constexpr int TC_NW = 4;                          // MMA issuer warps (tiles are dealt round-robin)
+constexpr int TC_THREADS = (4 + 1 + TC_NW) * 32;  // 4 epilogue warps, 1 TMA producer, TC_NW issuers
+
 template <int ARCH>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map, const TcArgs a) {
   constexpr int C = 32;
   constexpr int W = (ARCH == 1) ? 64 : 32;   // conv output channels
@@ -101,21 +120,24 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
   uint64_t* full = bars;                  // [TC_MAX_R]
   uint64_t* empty = full + TC_MAX_R;      // [TC_MAX_R]
   uint64_t* cfull = empty + TC_MAX_R;     // [NCS] accumulator ready
-  uint64_t* cempty = cfull + 8;           // [NCS] accumulator drained
-  uint64_t* rempty = cempty + 8;          // [2] residual accumulator drained
-  uint64_t* wfull = rempty + 2;           // weights landed
-  uint32_t* tmem_slot = (uint32_t*)(wfull + 1);
+  uint64_t* wfull = cfull + 8;            // weights landed
+  // epi_done[w] = number of tiles whose accumulators epilogue warp w has finished reading.
+  // A monotonic counter (not an mbarrier parity) because several issuer warps wait on it
+  // from different distances: tile q may start once tile q - NCS is drained, and write the
+  // residual accumulator once tile q - 2 is drained.
+  volatile uint32_t* epi_done = (volatile uint32_t*)(wfull + 2);   // [4], 16-byte aligned
+  uint32_t* tmem_slot = (uint32_t*)(wfull + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TC_MAX_R; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < NCS; ++i) { mbar_init(&cfull[i], 1); mbar_init(&cempty[i], 4); }
-    mbar_init(&rempty[0], 4); mbar_init(&rempty[1], 4);
+    for (int i = 0; i < TC_MAX_R; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], TC_NW); }
+    for (int i = 0; i < NCS; ++i) mbar_init(&cfull[i], 1);
     mbar_init(wfull, 1);
+    for (int i = 0; i < 4; ++i) epi_done[i] = 0;
     fence_barrier_init();
   }
-  if (warp == 0) {
+  if (warp == 4) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -124,7 +146,7 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 4) {
     // ================================ TMA producer ================================
     if (elect_one()) {
       prefetch_tensormap(&in_map);
@@ -148,22 +170,43 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    // The whole warp walks the schedule with warp-uniform values (so the address math
-    // stays on the uniform datapath); only the tcgen05 instructions are predicated on
-    // one elected lane.
+  } else if (warp > 4) {
+    // ================================ MMA issuers ================================
+    // TC_NW warps; warp `wslot` owns the tiles whose running index q satisfies q % TC_NW == wslot
+    // (tiles are independent accumulators, so the warps only meet at the ring-slot release).
+    // The whole warp walks the schedule.  Per window ("step") the lanes work out in
+    // parallel which (tile, tap) batches complete in that window and build their
+    // descriptors; the batches are then issued one lane at a time (4 MMAs each), so the
+    // serial part per batch is only the tcgen05 instructions themselves.
+    const int wslot = warp - 5;
     const uint32_t leader = elect_one() ? 1u : 0u;
     constexpr uint32_t idesc_hi = make_idesc(FMT_F16, FMT_F16, 128, CW);   // B = [wh ; wl]
     constexpr uint32_t idesc_lo = make_idesc(FMT_F16, FMT_F16, 128, W);    // B = wh
     constexpr uint32_t idesc_rhi = make_idesc(FMT_F16, FMT_F16, 128, RW);
     constexpr uint32_t idesc_rlo = make_idesc(FMT_F16, FMT_F16, 128, C);
-    // descriptor = (constant high word, low word = 16-byte address | LBO bit); only the low word moves
-    const uint32_t desc_hi = (uint32_t)(make_desc_sw128(0) >> 32);
+    static_assert((make_desc_sw128_hi()) == NASR_DESC_HI_SW128, "descriptor high word");
+    // descriptor low word = 16-byte address | LBO bit; only it moves
     const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t w_lo32 = ((smem_u32(wsm) & 0x3FFFFu) >> 4) | (1u << 16);
     const int k = a.k, d = a.d, mode = a.mode, R = a.R, km1 = a.k - 1;
     const uint32_t r_lo32 = w_lo32 + (uint32_t)(k >> 1) * (PAIR_BYTES >> 4) + (uint32_t)(k & 1) * 4u;
+    // lane m holds tap m = k-1-j (it looks m*d rows back): view start offset inside a slot
+    // (16-byte units), whether the view starts in the previous slot, and the weight tile
+    const int t_frac = (lane * d) & 127;
+    const uint32_t t_aoff = (mode == 0) ? (uint32_t)((128 - t_frac) & 127) * 8u : 0u;
+    const uint32_t t_prev = (mode == 0 && t_frac != 0) ? 1u : 0u;
+    const int t_j = km1 - lane;
+    const uint32_t t_blo = w_lo32 + (uint32_t)((t_j >> 1) * (PAIR_BYTES >> 4)) + (uint32_t)(t_j & 1) * 4u;
+    // lane qq holds the tap range [q_lo, q_hi] whose views END qq slots before the tile's own slot
+    int q_lo, q_hi;
+    if (mode == 0) {
+      q_lo = (lane * 128 + d - 1) / d;
+      q_hi = (lane * 128 + 127) / d;
+      if (q_hi > km1) q_hi = km1;
+    } else {
+      q_lo = lane;
+      q_hi = lane <= km1 ? lane : lane - 1;
+    }
     mbar_wait(wfull, 0);
     tc_fence_after();
     Sched s(a);
@@ -176,62 +219,79 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
       const int Gc = s.Gc;
       uint32_t started = 0;            // bit i: tile i of the group has received its first MMA
       for (int step = 0; step < nwin; ++step) {
+        const int wrel = step - lead;  // w - P0
+        const int prevpos = pos == 0 ? R - 1 : pos - 1;
+        // ---- which batches complete in this window: lane <-> (tile my_i, tap my_m) ----
+        int my_i = -1, my_m = 0, cnt = 0;
+        uint32_t my_first = 0, touched = 0;
+        if (mode == 0) {
+          for (int i = (wrel > 0 ? wrel : 0); i < Gc; ++i) {
+            const int qq = i - wrel;
+            if (qq > 31) break;
+            const int lo = __shfl_sync(0xffffffffu, q_lo, qq), hi = __shfl_sync(0xffffffffu, q_hi, qq);
+            const int n = hi - lo + 1;
+            if (n <= 0) { if (lo > km1) break; continue; }
+            if (((q0 + i) % TC_NW) != wslot) continue;
+            if (lane >= cnt && lane < cnt + n) {
+              my_i = i; my_m = hi - (lane - cnt);
+              my_first = (lane == cnt) && !((started >> i) & 1u);
+            }
+            touched |= 1u << i;
+            cnt += n;
+          }
+        } else {
+          const int i0 = wrel > 0 ? wrel : 0;
+          int i1 = wrel + km1; if (i1 > Gc - 1) i1 = Gc - 1;
+          // my tiles among i0..i1: i = ifirst + TC_NW * lane
+          int ifirst = i0 + ((wslot - ((q0 + i0) % TC_NW)) + TC_NW) % TC_NW;
+          cnt = ifirst <= i1 ? (i1 - ifirst) / TC_NW + 1 : 0;
+          if (lane < cnt) {
+            my_i = ifirst + TC_NW * lane; my_m = my_i - wrel;
+            my_first = !((started >> my_i) & 1u);
+            touched = 1u << my_i;
+          }
+          touched = __reduce_or_sync(0xffffffffu, touched);
+        }
+        started |= touched;
+        const bool valid = my_i >= 0;
+        const uint32_t aoff = __shfl_sync(0xffffffffu, t_aoff, my_m);
+        const uint32_t prv = __shfl_sync(0xffffffffu, t_prev, my_m);
+        const uint32_t blo = __shfl_sync(0xffffffffu, t_blo, my_m);
+        const uint32_t a_lo = ring_lo + (uint32_t)(prv ? prevpos : pos) * (TC_SLOT_BYTES >> 4) + aoff;
+        const int q = q0 + (valid ? my_i : 0);
+        const uint32_t first_mask = __ballot_sync(0xffffffffu, valid && my_first);
+        const uint32_t last_mask = __ballot_sync(0xffffffffu, valid && my_m == 0);
+
         mbar_wait(&full[pos], (full_phase >> pos) & 1u);
         full_phase ^= 1u << pos;
         tc_fence_after();
-        const int wrel = step - lead;  // w - P0
-        const int prevpos = pos == 0 ? R - 1 : pos - 1;
-        for (int i = (wrel > 0 ? wrel : 0); i < Gc; ++i) {
-          const int qq = i - wrel;     // P - w >= 0
-          int m_lo, m_hi;              // taps (m = k-1-j) of tile i whose view ends in this window
-          if (mode == 0) {
-            // taps with floor(m*d/128) == qq; d < 128 so they are contiguous in m
-            m_lo = (qq * 128 + d - 1) / d;
-            m_hi = (qq * 128 + 127) / d;
-            if (m_hi > km1) m_hi = km1;
-          } else {
-            m_lo = m_hi = qq;
-            if (qq > km1) break;
+        // ---- issue: batch e (4 MMAs) is broadcast from lane e and issued by the elected lane ----
+        for (int e = 0; e < cnt; ++e) {
+          const uint32_t a_e = __shfl_sync(0xffffffffu, a_lo, e);
+          const uint32_t b_e = __shfl_sync(0xffffffffu, blo, e);
+          const int q_e = __shfl_sync(0xffffffffu, q, e);
+          const int cs_e = q_e % NCS;
+          const uint32_t d_e = tmem + (uint32_t)(cs_e * CW);
+          uint32_t acc_e = 1u;
+          if ((first_mask >> e) & 1u) {
+            acc_e = 0u;
+            wait_drained(epi_done, q_e - NCS + 1);   // accumulator slot of tile q_e - NCS is free
           }
-          if (m_lo > m_hi) { if (mode == 0 && m_lo > km1) break; continue; }
-          const int q = q0 + i;
-          const int cs = q % NCS;
-          const uint32_t dcol = tmem + (uint32_t)(cs * CW);
-          if (!((started >> i) & 1u)) {
-            mbar_wait(&cempty[cs], (uint32_t)(((q / NCS) & 1) ^ 1));
-            tc_fence_after();
-          }
-          int sft = m_hi * d;          // rows this tap looks back
-          for (int m = m_hi; m >= m_lo; --m, sft -= d) {
-            const int j = km1 - m;
-            uint32_t a_lo;
-            if (mode == 0) {
-              const int frac = sft & 127;                       // view starts 128-frac rows into the previous slot
-              const int pa = frac ? prevpos : pos;
-              a_lo = ring_lo + (uint32_t)pa * (TC_SLOT_BYTES >> 4) + (uint32_t)((128 - frac) & 127) * 8u;
-            } else {
-              a_lo = ring_lo + (uint32_t)pos * (TC_SLOT_BYTES >> 4);
-            }
-            const uint32_t b_lo = w_lo32 + (uint32_t)(j >> 1) * (PAIR_BYTES >> 4) + (uint32_t)(j & 1) * 4u;
-            const uint32_t acc = (started >> i) & 1u;
-            started |= 1u << i;
-            // +2 = next 16-channel slice (32 B), +4 = lo half of the row (64 B)
-            umma_f16_lo(dcol, a_lo, b_lo, desc_hi, idesc_hi, acc, leader);
-            umma_f16_lo(dcol, a_lo + 2, b_lo + 2, desc_hi, idesc_hi, 1, leader);
-            umma_f16_lo(dcol, a_lo + 4, b_lo, desc_hi, idesc_lo, 1, leader);
-            umma_f16_lo(dcol, a_lo + 6, b_lo + 2, desc_hi, idesc_lo, 1, leader);
-            if (m == 0) {
-              // residual 1x1 on the unshifted view (weights stored as tap index k)
-              const int rs = q & 1;
-              mbar_wait(&rempty[rs], (uint32_t)(((q >> 1) & 1) ^ 1));
-              tc_fence_after();
-              const uint32_t rcol = tmem + (uint32_t)(NCS * CW + rs * RW);
-              umma_f16_lo(rcol, a_lo, r_lo32, desc_hi, idesc_rhi, 0, leader);
-              umma_f16_lo(rcol, a_lo + 2, r_lo32 + 2, desc_hi, idesc_rhi, 1, leader);
-              umma_f16_lo(rcol, a_lo + 4, r_lo32, desc_hi, idesc_rlo, 1, leader);
-              umma_f16_lo(rcol, a_lo + 6, r_lo32 + 2, desc_hi, idesc_rlo, 1, leader);
-              umma_commit_if(&cfull[cs], leader);   // tile complete: accumulators ready for the epilogue
-            }
+          // +2 = next 16-channel slice (32 B), +4 = lo half of the row (64 B)
+          umma_f16_imm<idesc_hi>(d_e, a_e, b_e, acc_e, leader);
+          umma_f16_imm<idesc_hi>(d_e, a_e + 2, b_e + 2, 1, leader);
+          umma_f16_imm<idesc_lo>(d_e, a_e + 4, b_e, 1, leader);
+          umma_f16_imm<idesc_lo>(d_e, a_e + 6, b_e + 2, 1, leader);
+          if ((last_mask >> e) & 1u) {
+            // residual 1x1 on the unshifted view (weights stored as tap index k), then hand over
+            const int rs = q_e & 1;
+            wait_drained(epi_done, q_e - 1);         // residual slot of tile q_e - 2 is free
+            const uint32_t rcol = tmem + (uint32_t)(NCS * CW + rs * RW);
+            umma_f16_imm<idesc_rhi>(rcol, a_e, r_lo32, 0, leader);
+            umma_f16_imm<idesc_rhi>(rcol, a_e + 2, r_lo32 + 2, 1, leader);
+            umma_f16_imm<idesc_rlo>(rcol, a_e + 4, r_lo32, 1, leader);
+            umma_f16_imm<idesc_rlo>(rcol, a_e + 6, r_lo32 + 2, 1, leader);
+            umma_commit_if(&cfull[cs_e], leader);   // tile complete: accumulators ready for the epilogue
           }
         }
         // release ring slots whose last reader has been issued
@@ -247,7 +307,7 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
     }
     __syncwarp();
   } else {
-    // ================================ epilogue (warps 2..5) ================================
+    // ================================ epilogue (warps 0..3) ================================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;            // row of the tile owned by this thread
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
@@ -303,8 +363,9 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&cempty[cs]);
-          mbar_arrive(&rempty[rs]);
+          asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32((const void*)(epi_done + quad))),
+                       "r"((uint32_t)(q + 1))
+                       : "memory");
         }
 #pragma unroll
         for (int c = 0; c < C; ++c) o[c] += (__uint_as_float(u[c]) + __uint_as_float(v[c])) * a.inv_sr;
@@ -351,7 +412,7 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (warp == 4) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -439,7 +500,7 @@ cudaError_t launch_tc_block(const TcLaunch& L, cudaStream_t s) {
       if (err != cudaSuccess) return err;
       set0 = true;
     }
-    tc_block_kernel<0><<<(unsigned)grid, 192, smem, s>>>(in_map, w_map, a);
+    tc_block_kernel<0><<<(unsigned)grid, TC_THREADS, smem, s>>>(in_map, w_map, a);
   } else {
     static bool set1 = false;
     if (!set1) {
@@ -447,7 +508,7 @@ cudaError_t launch_tc_block(const TcLaunch& L, cudaStream_t s) {
       if (err != cudaSuccess) return err;
       set1 = true;
     }
-    tc_block_kernel<1><<<(unsigned)grid, 192, smem, s>>>(in_map, w_map, a);
+    tc_block_kernel<1><<<(unsigned)grid, TC_THREADS, smem, s>>>(in_map, w_map, a);
   }
   return cudaGetLastError();
 }
