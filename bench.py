@@ -202,12 +202,8 @@ def main():
 
     model, arch, kw, T = build_model(args.workload)
     # one-time weight broadcast over NCCL: every rank ends up with rank 0's blob
-    if world > 1:
-        blob = model.weight_blob().to(dev)
-        if rank != 0:
-            blob.zero_()
-        dist.broadcast(blob, src=0)
-        model.load_weight_blob(blob.cpu())
+    from neural_audio_spring_reverb_b200.distributed import broadcast_weights
+    broadcast_weights(model, src=0, device=dev)
     model = model.to(dev).eval()
     eng = model._engine()
 
