@@ -36,40 +36,46 @@ def _stale() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build_native(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a and link the shared library."""
-    if not force and not _stale():
+def build_native(force: bool = False, verbose: bool = False, extra_flags=(), out: Path = None) -> Path:
+    """Compile every CUDA source for sm_100a and link the shared library.
+    `extra_flags` / `out` build a tuning variant next to the default library (dev use)."""
+    variant = out is not None
+    out = Path(out) if variant else LIB_PATH
+    if not variant and not force and not _stale():
         return LIB_PATH
     nvcc = _nvcc()
-    obj_dir = PKG_DIR / "build"
-    obj_dir.mkdir(exist_ok=True)
+    obj_dir = PKG_DIR / "build" / (out.stem if variant else "default")
+    obj_dir.mkdir(parents=True, exist_ok=True)
     srcs = [s for s in SOURCES if (CSRC / s).exists()]
     procs = []
     for s in srcs:
         obj = obj_dir / (s + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / s), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", str(CSRC / s), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
         procs.append((s, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for s, obj, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {s}:\n{out}")
-        if verbose and out:
-            print(out)
+            raise RuntimeError(f"nvcc failed on {s}:\n{log}")
+        if verbose and log:
+            print(log)
         objs.append(str(obj))
-    tmp = LIB_PATH.with_suffix(".so.tmp")
+    tmp = Path(str(out) + ".tmp")
     cmd = [nvcc, "-shared", "-o", str(tmp), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
            "-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
-    os.replace(tmp, LIB_PATH)
-    return LIB_PATH
+    os.replace(tmp, out)
+    return out
 
 
 if __name__ == "__main__":
-    path = build_native(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    path = build_native(force="--force" in sys.argv, verbose="-v" in sys.argv, extra_flags=extra,
+                        out=Path(outs[0]) if outs else None)
     print(path)

@@ -33,6 +33,14 @@
 #include "tc_block.cuh"
 #include <cuda_fp16.h>
 #include <cmath>
+#include <cstdlib>
+
+#ifndef TC_NW_TCN
+#define TC_NW_TCN 8
+#endif
+#ifndef TC_NW_GCN
+#define TC_NW_GCN 3
+#endif
 
 namespace nasr {
 using namespace sm100;
@@ -43,23 +51,43 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Gate non-linearities of GCN (custom_layers.py:106-107) on the MUFU ex2/rcp path: absolute
+// error ~1e-7 (outputs are O(1)), far inside the 1e-4 parity budget, ~8 instructions each.
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = __expf(2.0f * x);            // inf for large x -> 1 - 0; 0 for very negative x -> 1 - 2
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  const float e = __expf(-x);
+  return e > 1e30f ? 0.0f : __fdividef(1.0f, 1.0f + e);
+}
+
 __device__ __forceinline__ long long floordiv(long long a, long long b) {
   long long q = a / b;
   return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
 }
 
-// issuer side: wait until all four epilogue warps have drained at least `need` tiles
+// issuer side: wait until every tile with running index < need has been drained by the epilogue.
+// Epilogue set e (warps 4e..4e+3) drains the tiles with q % ESETS == e; each warp publishes
+// (index of the last tile it finished) + 1 in epi_done[warp].
+template <int ESETS>
 __device__ __forceinline__ void wait_drained(volatile uint32_t* epi_done, int need) {
   if (need <= 0) return;
   const uint32_t addr = sm100::smem_u32((const void*)epi_done);
   while (true) {
-    uint32_t d0, d1, d2, d3;
-    asm volatile("ld.acquire.cta.shared::cta.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3)
-                 : "r"(addr)
-                 : "memory");
-    const uint32_t m01 = d0 < d1 ? d0 : d1, m23 = d2 < d3 ? d2 : d3;
-    if ((int)(m01 < m23 ? m01 : m23) >= need) break;
+    bool ok = true;
+#pragma unroll
+    for (int e = 0; e < ESETS; ++e) {
+      // largest tile < need owned by set e is need - 1 - ((need - 1 - e) mod ESETS); none if negative
+      const int last = need - 1 - (((need - 1 - e) % ESETS + ESETS) % ESETS);
+      uint32_t d0, d1, d2, d3;
+      asm volatile("ld.acquire.cta.shared::cta.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3)
+                   : "r"(addr + 16 * e)
+                   : "memory");
+      ok = ok && (last < 0 || (int)min(min(d0, d1), min(d2, d3)) >= last + 1);
+    }
+    if (ok) break;
   }
   sm100::tc_fence_after();
 }
@@ -99,11 +127,16 @@ struct Sched {
   }
 };
 
-constexpr int TC_NW = 4;                          // MMA issuer warps (tiles are dealt round-robin)
-constexpr int TC_THREADS = (4 + 1 + TC_NW) * 32;  // 4 epilogue warps, 1 TMA producer, TC_NW issuers
+// Warp layout, per architecture: ESETS epilogue sets of 4 warps (set e drains the tiles with
+// q % ESETS == e), then 1 TMA producer warp, then NW MMA issuer warps (tile q -> issuer q % NW).
+// TCN is issue-bound (N = 32/64 instructions), GCN epilogue-bound (tanh, sigmoid per element).
+template <int ARCH> struct TcCfg;
+template <> struct TcCfg<0> { static constexpr int ESETS = 1, NW = TC_NW_TCN; };
+template <> struct TcCfg<1> { static constexpr int ESETS = 2, NW = TC_NW_GCN; };
+template <int ARCH> constexpr int tc_threads() { return (4 * TcCfg<ARCH>::ESETS + 1 + TcCfg<ARCH>::NW) * 32; }
 
 template <int ARCH>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads<ARCH>(), 1)
 tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map, const TcArgs a) {
   constexpr int C = 32;
   constexpr int W = (ARCH == 1) ? 64 : 32;   // conv output channels
@@ -111,6 +144,8 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
   constexpr int RW = 2 * C;                  // residual accumulator columns
   constexpr int NCS = (512 - 2 * RW) / CW;   // conv accumulator slots: 6 (TCN) / 3 (GCN)
   constexpr int PAIR_BYTES = CW * 128;       // one weight tap pair: 2W rows x 128 B
+  constexpr int ESETS = TcCfg<ARCH>::ESETS, TC_NW = TcCfg<ARCH>::NW;
+  constexpr int TC_EPI_WARPS = 4 * ESETS, TC_PRODUCER_WARP = TC_EPI_WARPS;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -125,8 +160,8 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
   // A monotonic counter (not an mbarrier parity) because several issuer warps wait on it
   // from different distances: tile q may start once tile q - NCS is drained, and write the
   // residual accumulator once tile q - 2 is drained.
-  volatile uint32_t* epi_done = (volatile uint32_t*)(wfull + 2);   // [4], 16-byte aligned
-  uint32_t* tmem_slot = (uint32_t*)(wfull + 4);
+  volatile uint32_t* epi_done = (volatile uint32_t*)(wfull + 2);   // [8], 16-byte aligned: set A (even tiles), set B (odd)
+  uint32_t* tmem_slot = (uint32_t*)(wfull + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -134,10 +169,10 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
     for (int i = 0; i < TC_MAX_R; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], TC_NW); }
     for (int i = 0; i < NCS; ++i) mbar_init(&cfull[i], 1);
     mbar_init(wfull, 1);
-    for (int i = 0; i < 4; ++i) epi_done[i] = 0;
+    for (int i = 0; i < TC_EPI_WARPS; ++i) epi_done[i] = 0;
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == TC_PRODUCER_WARP) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -146,7 +181,7 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == TC_PRODUCER_WARP) {
     // ================================ TMA producer ================================
     if (elect_one()) {
       prefetch_tensormap(&in_map);
@@ -170,7 +205,7 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
       }
     }
     __syncwarp();
-  } else if (warp > 4) {
+  } else if (warp > TC_PRODUCER_WARP) {
     // ================================ MMA issuers ================================
     // TC_NW warps; warp `wslot` owns the tiles whose running index q satisfies q % TC_NW == wslot
     // (tiles are independent accumulators, so the warps only meet at the ring-slot release).
@@ -178,8 +213,13 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
     // parallel which (tile, tap) batches complete in that window and build their
     // descriptors; the batches are then issued one lane at a time (4 MMAs each), so the
     // serial part per batch is only the tcgen05 instructions themselves.
-    const int wslot = warp - 5;
-    const uint32_t leader = elect_one() ? 1u : 0u;
+    const int wslot = warp - TC_PRODUCER_WARP - 1;
+    const uint32_t leader_commit = elect_one() ? 1u : 0u;
+#ifdef NASR_TC_DEBUG
+    const uint32_t leader = (a.dbg & 1) ? 0u : leader_commit;   // dev: schedule walk without MMAs
+#else
+    const uint32_t leader = leader_commit;
+#endif
     constexpr uint32_t idesc_hi = make_idesc(FMT_F16, FMT_F16, 128, CW);   // B = [wh ; wl]
     constexpr uint32_t idesc_lo = make_idesc(FMT_F16, FMT_F16, 128, W);    // B = wh
     constexpr uint32_t idesc_rhi = make_idesc(FMT_F16, FMT_F16, 128, RW);
@@ -190,13 +230,6 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
     const uint32_t w_lo32 = ((smem_u32(wsm) & 0x3FFFFu) >> 4) | (1u << 16);
     const int k = a.k, d = a.d, mode = a.mode, R = a.R, km1 = a.k - 1;
     const uint32_t r_lo32 = w_lo32 + (uint32_t)(k >> 1) * (PAIR_BYTES >> 4) + (uint32_t)(k & 1) * 4u;
-    // lane m holds tap m = k-1-j (it looks m*d rows back): view start offset inside a slot
-    // (16-byte units), whether the view starts in the previous slot, and the weight tile
-    const int t_frac = (lane * d) & 127;
-    const uint32_t t_aoff = (mode == 0) ? (uint32_t)((128 - t_frac) & 127) * 8u : 0u;
-    const uint32_t t_prev = (mode == 0 && t_frac != 0) ? 1u : 0u;
-    const int t_j = km1 - lane;
-    const uint32_t t_blo = w_lo32 + (uint32_t)((t_j >> 1) * (PAIR_BYTES >> 4)) + (uint32_t)(t_j & 1) * 4u;
     // lane qq holds the tap range [q_lo, q_hi] whose views END qq slots before the tile's own slot
     int q_lo, q_hi;
     if (mode == 0) {
@@ -207,6 +240,8 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
       q_lo = lane;
       q_hi = lane <= km1 ? lane : lane - 1;
     }
+    // the deepest slot (counted back from a tile's own) that any tap still reaches into
+    const int qmax = (mode == 0) ? ((km1 * d) >> 7) : km1;
     mbar_wait(wfull, 0);
     tc_fence_after();
     Sched s(a);
@@ -218,88 +253,72 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
       const int lead = nwin - s.Gc;    // windows before the group's first tile
       const int Gc = s.Gc;
       uint32_t started = 0;            // bit i: tile i of the group has received its first MMA
+      const int i_first = ((wslot - q0) % TC_NW + TC_NW) % TC_NW;   // my tiles: i_first, i_first + TC_NW, ...
       for (int step = 0; step < nwin; ++step) {
         const int wrel = step - lead;  // w - P0
         const int prevpos = pos == 0 ? R - 1 : pos - 1;
-        // ---- which batches complete in this window: lane <-> (tile my_i, tap my_m) ----
-        int my_i = -1, my_m = 0, cnt = 0;
-        uint32_t my_first = 0, touched = 0;
-        if (mode == 0) {
-          for (int i = (wrel > 0 ? wrel : 0); i < Gc; ++i) {
-            const int qq = i - wrel;
-            if (qq > 31) break;
-            const int lo = __shfl_sync(0xffffffffu, q_lo, qq), hi = __shfl_sync(0xffffffffu, q_hi, qq);
-            const int n = hi - lo + 1;
-            if (n <= 0) { if (lo > km1) break; continue; }
-            if (((q0 + i) % TC_NW) != wslot) continue;
-            if (lane >= cnt && lane < cnt + n) {
-              my_i = i; my_m = hi - (lane - cnt);
-              my_first = (lane == cnt) && !((started >> i) & 1u);
+        // Every issuer warp walks every window (it has to count on the ring barriers), so the
+        // common case "nothing of mine here" must stay cheap: only own tiles are looked at, and
+        // only while the window lies inside their tap span [0, qmax] slots back.
+        bool waited = false;
+        for (int i = i_first; i < Gc; i += TC_NW) {
+          const int qq = i - wrel;               // how many slots the window lies before the tile's own
+          if (qq < 0) continue;
+          if (qq > qmax) break;
+          int m_lo = qq, m_hi = qq;              // mode D: exactly tap m = qq
+          if (mode == 0) {                       // mode C: taps with floor(m*d/128) == qq
+            m_lo = __shfl_sync(0xffffffffu, q_lo, qq);
+            m_hi = __shfl_sync(0xffffffffu, q_hi, qq);
+          }
+          if (m_lo > m_hi) continue;
+          if (!waited) {
+            mbar_wait(&full[pos], (full_phase >> pos) & 1u);
+            tc_fence_after();
+            waited = true;
+          }
+          const int q = q0 + i;
+          const int cs = q % NCS;
+          const uint32_t dcol = tmem + (uint32_t)(cs * CW);
+          uint32_t acc = 1u;
+          if (!((started >> i) & 1u)) {
+            started |= 1u << i;
+            acc = 0u;
+            wait_drained<ESETS>(epi_done, q - NCS + 1);   // accumulator slot of tile q - NCS is free
+          }
+          int sft = m_hi * d;                    // rows tap m looks back
+          for (int m = m_hi; m >= m_lo; --m, sft -= d) {
+            const int j = km1 - m;
+            const int frac = (mode == 0) ? (sft & 127) : 0;   // view starts 128 - frac rows into the previous slot
+            const uint32_t a_lo = ring_lo + (uint32_t)(frac ? prevpos : pos) * (TC_SLOT_BYTES >> 4) +
+                                  (uint32_t)((128 - frac) & 127) * 8u;
+            const uint32_t b_lo = w_lo32 + (uint32_t)(j >> 1) * (PAIR_BYTES >> 4) + (uint32_t)(j & 1) * 4u;
+            // +2 = next 16-channel slice (32 B), +4 = lo half of the row (64 B)
+            umma_f16_imm<idesc_hi>(dcol, a_lo, b_lo, acc, leader);
+            umma_f16_imm<idesc_hi>(dcol, a_lo + 2, b_lo + 2, 1, leader);
+            umma_f16_imm<idesc_lo>(dcol, a_lo + 4, b_lo, 1, leader);
+            umma_f16_imm<idesc_lo>(dcol, a_lo + 6, b_lo + 2, 1, leader);
+            acc = 1u;
+            if (m == 0) {
+              // residual 1x1 on the unshifted view (weights stored as tap index k), then hand over
+              const int rs = q & 1;
+              wait_drained<ESETS>(epi_done, q - 1);       // residual slot of tile q - 2 is free
+              const uint32_t rcol = tmem + (uint32_t)(NCS * CW + rs * RW);
+              umma_f16_imm<idesc_rhi>(rcol, a_lo, r_lo32, 0, leader);
+              umma_f16_imm<idesc_rhi>(rcol, a_lo + 2, r_lo32 + 2, 1, leader);
+              umma_f16_imm<idesc_rlo>(rcol, a_lo + 4, r_lo32, 1, leader);
+              umma_f16_imm<idesc_rlo>(rcol, a_lo + 6, r_lo32 + 2, 1, leader);
+              umma_commit_if(&cfull[cs], leader_commit);   // tile complete: accumulators ready for the epilogue
             }
-            touched |= 1u << i;
-            cnt += n;
           }
-        } else {
-          const int i0 = wrel > 0 ? wrel : 0;
-          int i1 = wrel + km1; if (i1 > Gc - 1) i1 = Gc - 1;
-          // my tiles among i0..i1: i = ifirst + TC_NW * lane
-          int ifirst = i0 + ((wslot - ((q0 + i0) % TC_NW)) + TC_NW) % TC_NW;
-          cnt = ifirst <= i1 ? (i1 - ifirst) / TC_NW + 1 : 0;
-          if (lane < cnt) {
-            my_i = ifirst + TC_NW * lane; my_m = my_i - wrel;
-            my_first = !((started >> my_i) & 1u);
-            touched = 1u << my_i;
-          }
-          touched = __reduce_or_sync(0xffffffffu, touched);
         }
-        started |= touched;
-        const bool valid = my_i >= 0;
-        const uint32_t aoff = __shfl_sync(0xffffffffu, t_aoff, my_m);
-        const uint32_t prv = __shfl_sync(0xffffffffu, t_prev, my_m);
-        const uint32_t blo = __shfl_sync(0xffffffffu, t_blo, my_m);
-        const uint32_t a_lo = ring_lo + (uint32_t)(prv ? prevpos : pos) * (TC_SLOT_BYTES >> 4) + aoff;
-        const int q = q0 + (valid ? my_i : 0);
-        const uint32_t first_mask = __ballot_sync(0xffffffffu, valid && my_first);
-        const uint32_t last_mask = __ballot_sync(0xffffffffu, valid && my_m == 0);
-
-        mbar_wait(&full[pos], (full_phase >> pos) & 1u);
+        if (!waited) mbar_wait(&full[pos], (full_phase >> pos) & 1u);   // keep pace with the ring
         full_phase ^= 1u << pos;
-        tc_fence_after();
-        // ---- issue: batch e (4 MMAs) is broadcast from lane e and issued by the elected lane ----
-        for (int e = 0; e < cnt; ++e) {
-          const uint32_t a_e = __shfl_sync(0xffffffffu, a_lo, e);
-          const uint32_t b_e = __shfl_sync(0xffffffffu, blo, e);
-          const int q_e = __shfl_sync(0xffffffffu, q, e);
-          const int cs_e = q_e % NCS;
-          const uint32_t d_e = tmem + (uint32_t)(cs_e * CW);
-          uint32_t acc_e = 1u;
-          if ((first_mask >> e) & 1u) {
-            acc_e = 0u;
-            wait_drained(epi_done, q_e - NCS + 1);   // accumulator slot of tile q_e - NCS is free
-          }
-          // +2 = next 16-channel slice (32 B), +4 = lo half of the row (64 B)
-          umma_f16_imm<idesc_hi>(d_e, a_e, b_e, acc_e, leader);
-          umma_f16_imm<idesc_hi>(d_e, a_e + 2, b_e + 2, 1, leader);
-          umma_f16_imm<idesc_lo>(d_e, a_e + 4, b_e, 1, leader);
-          umma_f16_imm<idesc_lo>(d_e, a_e + 6, b_e + 2, 1, leader);
-          if ((last_mask >> e) & 1u) {
-            // residual 1x1 on the unshifted view (weights stored as tap index k), then hand over
-            const int rs = q_e & 1;
-            wait_drained(epi_done, q_e - 1);         // residual slot of tile q_e - 2 is free
-            const uint32_t rcol = tmem + (uint32_t)(NCS * CW + rs * RW);
-            umma_f16_imm<idesc_rhi>(rcol, a_e, r_lo32, 0, leader);
-            umma_f16_imm<idesc_rhi>(rcol, a_e + 2, r_lo32 + 2, 1, leader);
-            umma_f16_imm<idesc_rlo>(rcol, a_e + 4, r_lo32, 1, leader);
-            umma_f16_imm<idesc_rlo>(rcol, a_e + 6, r_lo32 + 2, 1, leader);
-            umma_commit_if(&cfull[cs_e], leader);   // tile complete: accumulators ready for the epilogue
-          }
-        }
         // release ring slots whose last reader has been issued
         if (mode == 0) {
-          if (step > 0) umma_commit_if(&empty[prevpos], leader);
-          if (step == nwin - 1) umma_commit_if(&empty[pos], leader);
+          if (step > 0) umma_commit_if(&empty[prevpos], leader_commit);
+          if (step == nwin - 1) umma_commit_if(&empty[pos], leader_commit);
         } else {
-          umma_commit_if(&empty[pos], leader);
+          umma_commit_if(&empty[pos], leader_commit);
         }
         pos = (pos + 1 == R) ? 0 : pos + 1;
       }
@@ -307,7 +326,9 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
     }
     __syncwarp();
   } else {
-    // ================================ epilogue (warps 0..3) ================================
+    // ================================ epilogue (warps 0..7) ================================
+    // epilogue set e = warp / 4 drains the tiles with q % ESETS == e
+    const int eset = warp >> 2;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;            // row of the tile owned by this thread
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
@@ -315,6 +336,7 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
     long long q = 0;
     while (s.next(a)) {
       for (int i = 0; i < s.Gc; ++i, ++q) {
+        if ((int)(q % ESETS) != eset) continue;
         const int cs = (int)(q % NCS), rs = (int)(q & 1);
         mbar_wait(&cfull[cs], (uint32_t)((q / NCS) & 1));
         tc_fence_after();
@@ -327,6 +349,19 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
         const uint32_t rcol = lane_base + (uint32_t)(NCS * CW + rs * RW);
         float o[C];
         uint32_t u[32], v[32];
+#ifdef NASR_TC_DEBUG
+        if (a.dbg & 2) {   // dev: drain without math / stores
+          tmem_ld_32x32(dcol, u);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32((const void*)(epi_done + warp))),
+                         "r"((uint32_t)(q + 1))
+                         : "memory");
+          continue;
+        }
+#endif
         if (ARCH == 0) {
           tmem_ld_32x32(dcol, u);
           tmem_ld_32x32(dcol + W, v);
@@ -344,7 +379,7 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
 #pragma unroll
           for (int c = 0; c < C; ++c) {
             const float z = __uint_as_float(u[c]) + __uint_as_float(v[c]);
-            o[c] = tanhf(fmaf(z, __ldg(sc + c) * a.inv_sw, __ldg(sh + c)));
+            o[c] = fast_tanh(fmaf(z, __ldg(sc + c) * a.inv_sw, __ldg(sh + c)));
           }
           tmem_ld_32x32(dcol + C, u);
           tmem_ld_32x32(dcol + W + C, v);
@@ -353,7 +388,7 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
           for (int c = 0; c < C; ++c) {
             const float z = __uint_as_float(u[c]) + __uint_as_float(v[c]);
             const float g = fmaf(z, __ldg(sc + C + c) * a.inv_sw, __ldg(sh + C + c));
-            o[c] *= 1.0f / (1.0f + expf(-g));
+            o[c] *= fast_sigmoid(g);
           }
         }
         tmem_ld_32x32(rcol, u);
@@ -363,7 +398,7 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32((const void*)(epi_done + quad))),
+          asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32((const void*)(epi_done + warp))),
                        "r"((uint32_t)(q + 1))
                        : "memory");
         }
@@ -412,7 +447,7 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 512);
+  if (warp == TC_PRODUCER_WARP) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -470,6 +505,11 @@ cudaError_t launch_tc_block(const TcLaunch& L, cudaStream_t s) {
   if (a.B <= 0 || a.T <= 0) return cudaSuccess;
   const int W = L.arch == 1 ? 64 : 32;
   a.pairs = (a.k + 2) / 2;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("NASR_TC_DBG"); dbg = e ? atoi(e) : 0; }
+    a.dbg = dbg;
+  }
   int R = TC_MAX_R;
   while (R > 3 && tc_smem_bytes(L.arch, a.k, R) > 227 * 1024) --R;
   if (tc_smem_bytes(L.arch, a.k, R) > 227 * 1024) return cudaErrorInvalidConfiguration;
@@ -500,7 +540,7 @@ cudaError_t launch_tc_block(const TcLaunch& L, cudaStream_t s) {
       if (err != cudaSuccess) return err;
       set0 = true;
     }
-    tc_block_kernel<0><<<(unsigned)grid, TC_THREADS, smem, s>>>(in_map, w_map, a);
+    tc_block_kernel<0><<<(unsigned)grid, tc_threads<0>(), smem, s>>>(in_map, w_map, a);
   } else {
     static bool set1 = false;
     if (!set1) {
@@ -508,7 +548,7 @@ cudaError_t launch_tc_block(const TcLaunch& L, cudaStream_t s) {
       if (err != cudaSuccess) return err;
       set1 = true;
     }
-    tc_block_kernel<1><<<(unsigned)grid, TC_THREADS, smem, s>>>(in_map, w_map, a);
+    tc_block_kernel<1><<<(unsigned)grid, tc_threads<1>(), smem, s>>>(in_map, w_map, a);
   }
   return cudaGetLastError();
 }
