@@ -98,7 +98,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -107,9 +107,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None, timed=None):
+        """Median SM clock over the samples taken while the GPU ran this workload
+        (t_begin..t_end); `timed` = (start, end) of the K timed steps, reported separately."""
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -119,16 +121,23 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        in_timed = 0
+        for ts, r in self.rows:
+            if (t_begin is not None and ts < t_begin) or (t_end is not None and ts > t_end):
+                continue
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
                 for nme, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
+                if timed and timed[0] <= ts <= timed[1]:
+                    in_timed += 1
             except Exception:
                 continue
-        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm), samples_in_timed_steps=in_timed,
+                    window="warm-up + timed steps + the same forward looped for >= 1.5 s (nvidia-smi -lms 50)")
 
 
 def cpu_reference_arm(args):
@@ -221,23 +230,32 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident timing (value) ----
-    for _ in range(args.warmup):
-        y = model(x, cond)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    t_load0 = time.perf_counter()
+    for _ in range(args.warmup):
+        y = model(x, cond)
+    barrier()
     l0 = eng.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    t_timed0 = time.perf_counter()
     for s, e in ev:
         flush.zero_()                      # L2 flush between timed iterations
         s.record()
         y = model(x, cond)
         e.record()
     barrier()
+    t_timed1 = time.perf_counter()
     launches = eng.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    # the timed region of this workload is milliseconds long - too short for nvidia-smi to see -
+    # so keep the identical forward running (untimed) until the sampler has a usable window
+    while time.perf_counter() - t_load0 < 1.5:
+        for _ in range(8):
+            y = model(x, cond)
+        torch.cuda.synchronize(dev)
+    clocks = sampler.stop(t_load0, time.perf_counter(), (t_timed0, t_timed1)) if rank == 0 else None
     step_ms = [s.elapsed_time(e) for s, e in ev]
     total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
     if world > 1:

@@ -53,8 +53,7 @@ cudaError_t launch_first_block(const BlockArgs& a, const float* w0, int sm_count
 
 // fold: scale/shift[b][packed(w)] for one block (custom_layers.py:32-42 folded with conv bias)
 struct FoldArgs {
-  const float* cond;       // [B][cond_dim] or nullptr
-  int B, cond_dim, W, Wp, has_film;
+  int cond_dim, W, Wp, has_film;
   const float* conv_bias;  // [W]
   const float* ad_w;       // [2W][cond_dim]
   const float* ad_b;       // [2W]
@@ -63,7 +62,7 @@ struct FoldArgs {
   float eps;
   float* scale; float* shift;  // [B][Wp]
 };
-cudaError_t launch_fold(const FoldArgs* blocks_dev, int n_blocks, int B, int maxW, cudaStream_t s);
+cudaError_t launch_fold(const FoldArgs* blocks_dev, const float* cond, int n_blocks, int B, int maxW, cudaStream_t s);
 
 // streaming helpers
 cudaError_t launch_copy_rows(const void* src, long long src_clip_stride, long long src_row0,

@@ -44,9 +44,11 @@ struct nasr_engine {
   int device = 0, sm_count = 148;
   int C = 0, Cp = 0;
   std::vector<BlockState> blocks;
+  std::vector<TcMapCache> tc_cache;   // per block: last TMA descriptors
   float* wout = nullptr;  // [out_ch][Cp]
   FoldArgs* fold_dev = nullptr;
   int condCap = 0, condB = 0;
+  bool fold_valid = false;
   DevBuf plane[2];
   // streaming
   int streamB = 0;
@@ -182,6 +184,7 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
   cudaError_t err;
   if (allow_tc && bs.path == 1) {
     TcLaunch L{};
+    L.cache = &e->tc_cache[i];
     L.in = a.in; L.in_rows = a.in_rows; L.in_clip_stride_elems = a.in_clip_stride;
     L.wpacked = bs.wtc; L.arch = e->desc.arch; L.sm_count = e->sm_count;
     TcArgs& t = L.a;
@@ -273,6 +276,7 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
   const int n = desc->n_blocks, C = e->C, Cp = e->Cp, k = desc->kernel_size, cd = desc->cond_dim;
   const bool gcn = desc->arch == NASR_ARCH_GCN;
   e->blocks.resize(n);
+  e->tc_cache.resize(n);
   const float* p = w;
   std::vector<FoldArgs> fold(n);
   int rc = NASR_OK;
@@ -398,20 +402,24 @@ int nasr_set_cond(nasr_engine* e, const float* cond_dev, int B, void* stream) {
       NASR_CUDA(e, cudaMemset(b.shift, 0, (size_t)B * b.Wp * sizeof(float)));
     }
     e->condCap = B;
+    e->fold_valid = false;
   }
-  std::vector<FoldArgs> fold(n);
   int maxW = 0;
-  for (int i = 0; i < n; ++i) {
-    const BlockState& b = e->blocks[i];
-    FoldArgs& f = fold[i];
-    f.cond = cond_dev; f.B = B; f.cond_dim = e->desc.cond_dim; f.W = b.W; f.Wp = b.Wp; f.has_film = e->desc.has_film;
-    f.conv_bias = b.bias; f.ad_w = b.adw; f.ad_b = b.adb; f.bn_w = b.bnw; f.bn_b = b.bnb; f.bn_mean = b.mean; f.bn_var = b.var;
-    f.perm = b.perm; f.eps = e->desc.bn_eps; f.scale = b.scale; f.shift = b.shift;
-    if (b.W > maxW) maxW = b.W;
+  for (const auto& b : e->blocks) maxW = b.W > maxW ? b.W : maxW;
+  if (!e->fold_valid) {
+    // block descriptors only change when scale/shift are (re)allocated
+    std::vector<FoldArgs> fold(n);
+    for (int i = 0; i < n; ++i) {
+      const BlockState& b = e->blocks[i];
+      FoldArgs& f = fold[i];
+      f.cond_dim = e->desc.cond_dim; f.W = b.W; f.Wp = b.Wp; f.has_film = e->desc.has_film;
+      f.conv_bias = b.bias; f.ad_w = b.adw; f.ad_b = b.adb; f.bn_w = b.bnw; f.bn_b = b.bnb; f.bn_mean = b.mean; f.bn_var = b.var;
+      f.perm = b.perm; f.eps = e->desc.bn_eps; f.scale = b.scale; f.shift = b.shift;
+    }
+    NASR_CUDA(e, cudaMemcpy(e->fold_dev, fold.data(), sizeof(FoldArgs) * n, cudaMemcpyHostToDevice));
+    e->fold_valid = true;
   }
-  NASR_CUDA(e, cudaMemcpyAsync(e->fold_dev, fold.data(), sizeof(FoldArgs) * n, cudaMemcpyHostToDevice, s));
-  // the pageable staging copy above completes before return for non-pinned memory
-  NASR_CUDA(e, launch_fold(e->fold_dev, n, B, maxW, s));
+  NASR_CUDA(e, launch_fold(e->fold_dev, cond_dev, n, B, maxW, s));
   e->launches += 1;
   e->condB = B;
   return NASR_OK;

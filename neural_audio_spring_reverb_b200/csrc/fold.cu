@@ -13,7 +13,7 @@ namespace nasr {
 //   shift = g * ((bias[w] - bn.running_mean[w]) * inv + bn.bias[w]) + beta
 // Without FiLM (TCN with cond_dim == 0, tcn.py:63-64): scale = 1, shift = bias.
 // Computed in fp64 and rounded once.
-__global__ void fold_kernel(const FoldArgs* __restrict__ blocks) {
+__global__ void fold_kernel(const FoldArgs* __restrict__ blocks, const float* __restrict__ cond) {
   const FoldArgs f = blocks[blockIdx.x];
   const int b = blockIdx.y;
   for (int w = threadIdx.x; w < f.W; w += blockDim.x) {
@@ -21,7 +21,7 @@ __global__ void fold_kernel(const FoldArgs* __restrict__ blocks) {
     if (f.has_film) {
       double g = (double)f.ad_b[w], beta = (double)f.ad_b[f.W + w];
       for (int q = 0; q < f.cond_dim; ++q) {
-        const double c = (double)f.cond[(long long)b * f.cond_dim + q];
+        const double c = (double)cond[(long long)b * f.cond_dim + q];
         g += (double)f.ad_w[(long long)w * f.cond_dim + q] * c;
         beta += (double)f.ad_w[(long long)(f.W + w) * f.cond_dim + q] * c;
       }
@@ -35,11 +35,11 @@ __global__ void fold_kernel(const FoldArgs* __restrict__ blocks) {
   }
 }
 
-cudaError_t launch_fold(const FoldArgs* blocks_dev, int n_blocks, int B, int maxW, cudaStream_t s) {
+cudaError_t launch_fold(const FoldArgs* blocks_dev, const float* cond, int n_blocks, int B, int maxW, cudaStream_t s) {
   if (n_blocks <= 0 || B <= 0) return cudaSuccess;
   int threads = 32;
   while (threads < maxW && threads < 256) threads <<= 1;
-  fold_kernel<<<dim3(n_blocks, B), threads, 0, s>>>(blocks_dev);
+  fold_kernel<<<dim3(n_blocks, B), threads, 0, s>>>(blocks_dev, cond);
   return cudaGetLastError();
 }
 

@@ -526,11 +526,21 @@ cudaError_t launch_tc_block(const TcLaunch& L, cudaStream_t s) {
   a.chunk = (a.total + grid - 1) / grid;
   grid = (a.total + a.chunk - 1) / a.chunk;
 
-  CUtensorMap in_map, w_map;
-  if (!make_plane_map(&in_map, L.in, 64, (uint64_t)L.in_rows, (uint64_t)a.B, (uint64_t)L.in_clip_stride_elems, 128))
-    return cudaErrorInvalidValue;
-  if (!make_plane_map(&w_map, L.wpacked, 64, (uint64_t)a.pairs * 2 * W, 1, (uint64_t)a.pairs * 2 * W * 64, 2 * W))
-    return cudaErrorInvalidValue;
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  TcMapCache local;
+  TcMapCache* c = L.cache ? L.cache : &local;
+  CUtensorMap& in_map = *reinterpret_cast<CUtensorMap*>(c->in_map);
+  CUtensorMap& w_map = *reinterpret_cast<CUtensorMap*>(c->w_map);
+  if (c->in != L.in || c->in_rows != L.in_rows || c->in_stride != L.in_clip_stride_elems || c->B != a.B) {
+    if (!make_plane_map(&in_map, L.in, 64, (uint64_t)L.in_rows, (uint64_t)a.B, (uint64_t)L.in_clip_stride_elems, 128))
+      return cudaErrorInvalidValue;
+    c->in = L.in; c->in_rows = L.in_rows; c->in_stride = L.in_clip_stride_elems; c->B = a.B;
+  }
+  if (c->w != L.wpacked || c->pairs != a.pairs) {
+    if (!make_plane_map(&w_map, L.wpacked, 64, (uint64_t)a.pairs * 2 * W, 1, (uint64_t)a.pairs * 2 * W * 64, 2 * W))
+      return cudaErrorInvalidValue;
+    c->w = L.wpacked; c->pairs = a.pairs;
+  }
   const size_t smem = tc_smem_bytes(L.arch, a.k, R);
   cudaError_t err;
   if (L.arch == 0) {

@@ -35,7 +35,19 @@ struct TcArgs {
 };
 
 
+// TMA descriptors of the last launch of a block; re-encoding costs a few microseconds of host
+// time per descriptor, and repeated forwards of one shape reuse the same planes.
+struct TcMapCache {
+  alignas(64) unsigned char in_map[128];
+  alignas(64) unsigned char w_map[128];
+  const void* in = nullptr;
+  const void* w = nullptr;
+  long long in_rows = -1, in_stride = -1;
+  int B = -1, pairs = -1;
+};
+
 struct TcLaunch {
+  TcMapCache* cache = nullptr;      // optional
   const void* in;                   // SPLIT16 input plane (16-bit elements)
   long long in_rows;                // rows per clip
   long long in_clip_stride_elems;   // 16-bit elements between clips

@@ -72,9 +72,6 @@ class FusedNetMixin:
         out.append(self.out_net.weight)
         return out
 
-    def _nasr_key(self, tensors):
-        return tuple((t.data_ptr(), t._version) for t in tensors)
-
     def weight_blob(self) -> torch.Tensor:
         """Flat fp32 CPU tensor: what nasr_engine_create consumes (and what a
         multi-GPU launch broadcasts once over NCCL)."""
@@ -96,35 +93,44 @@ class FusedNetMixin:
                 off += n
 
     def _engine(self) -> "_native.Engine":
+        """The nasr_engine for the current parameters. Rebuilt when a parameter/buffer was
+        modified in place (tensor version counters) or replaced (.to(), load_state_dict)."""
+        cache = self.__dict__.get("_nasr_cache")
+        if cache is not None:
+            tensors, stamp, eng = cache
+            if stamp == sum(t._version for t in tensors) + tensors[0].data_ptr():
+                return eng
         tensors = self._nasr_tensors()
         dev = tensors[0].device
         if dev.type != "cuda":
             raise RuntimeError(
                 f"{type(self).__name__}: parameters are on {dev}; the forward runs only on a B200 "
                 "through libnasr_b200 (no CPU fallback) - move the model with .to('cuda:N')")
-        key = (dev.index if dev.index is not None else torch.cuda.current_device(),
-               self._nasr_key(tensors))
-        eng = self.__dict__.get("_nasr_engine")
-        if eng is None or self.__dict__.get("_nasr_engine_key") != key:
-            if eng is not None:
-                eng.close()
-            blob = self.weight_blob().numpy()
-            eng = _native.Engine(
-                arch=self._nasr_arch, n_blocks=self.n_blocks, in_ch=self.in_ch, out_ch=self.out_ch,
-                n_channels=self.channels[0], kernel_size=self.kernel_size, cond_dim=self.cond_dim,
-                has_film=self._nasr_has_film(), final_tanh=self._nasr_final_tanh,
-                dilations=self.dilations, weights=blob, device=key[0], path=_path_from_env(),
-                bn_eps=float(self.blocks[0].film.bn.eps) if self._nasr_has_film() else 1e-5)
-            self.__dict__["_nasr_engine"] = eng
-            self.__dict__["_nasr_engine_key"] = key
-            self.__dict__["_nasr_stream_B"] = None
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        old = self.__dict__.pop("_nasr_cache", None)
+        if old is not None:
+            old[2].close()
+        blob = self.weight_blob().numpy()
+        eng = _native.Engine(
+            arch=self._nasr_arch, n_blocks=self.n_blocks, in_ch=self.in_ch, out_ch=self.out_ch,
+            n_channels=self.channels[0], kernel_size=self.kernel_size, cond_dim=self.cond_dim,
+            has_film=self._nasr_has_film(), final_tanh=self._nasr_final_tanh,
+            dilations=self.dilations, weights=blob, device=index, path=_path_from_env(),
+            bn_eps=float(self.blocks[0].film.bn.eps) if self._nasr_has_film() else 1e-5)
+        stamp = sum(t._version for t in tensors) + tensors[0].data_ptr()
+        self.__dict__["_nasr_cache"] = (tensors, stamp, eng)
+        self.__dict__["_nasr_stream_B"] = None
         return eng
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float() may replace the parameter tensors: drop the engine
+        self.release_engine()
+        return super()._apply(fn, *args, **kwargs)
+
     def release_engine(self) -> None:
-        eng = self.__dict__.pop("_nasr_engine", None)
-        if eng is not None:
-            eng.close()
-        self.__dict__.pop("_nasr_engine_key", None)
+        cache = self.__dict__.pop("_nasr_cache", None)
+        if cache is not None:
+            cache[2].close()
 
     # ---- argument checks shared by forward / forward_chunk -----------------
     def _nasr_check(self, x: Tensor, cond: Optional[Tensor]):
@@ -190,7 +196,7 @@ class FusedNetMixin:
     def forward_chunk(self, x: Tensor, cond: Optional[Tensor] = None) -> Tensor:
         """Process the next chunk of a stream; history of the last (k-1)*d input
         samples of every block is carried across calls."""
-        if self.__dict__.get("_nasr_stream_B") != x.shape[0] or self.__dict__.get("_nasr_engine") is None:
+        if self.__dict__.get("_nasr_stream_B") != x.shape[0] or self.__dict__.get("_nasr_cache") is None:
             self.reset_stream(x.shape[0])
         return self._nasr_run(x, cond, True)
 
