@@ -133,6 +133,13 @@ NASR_API int nasr_forward(nasr_engine* e, const float* x_dev, float* y_dev, int 
 NASR_API int nasr_forward_profiled(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T,
                           void* stream, float* block_ms);
 
+/* The tcgen05 path keeps inter-block activations as fp16 hi + fp16 lo pairs; a value beyond
+ * +-65504 is clamped and flagged. nasr_forward_host checks the flag itself and transparently
+ * redoes the call on the fp32 kernels. After nasr_forward / nasr_forward_chunk (asynchronous)
+ * call this to find out: waits for `stream`, returns 1 if the last forward saturated (then
+ * re-create the engine with path = NASR_PATH_FP32), 0 if not, < 0 on error. */
+NASR_API int nasr_saturated(nasr_engine* e, void* stream);
+
 /* Host-buffer forward: H2D(x, cond) -> set_cond -> forward -> D2H(y), all on
  * `stream`, then waits for completion. cond_host may be NULL when cond_dim == 0. */
 NASR_API int nasr_forward_host(nasr_engine* e, const float* x_host, const float* cond_host,

@@ -20,7 +20,7 @@ LIB_PATH = Path(os.environ.get("NASR_LIB") or Path(__file__).resolve().parent / 
 # every symbol include/nasr_b200.h declares
 EXPORTS = (
     "nasr_weight_count", "nasr_engine_create", "nasr_engine_destroy", "nasr_last_error",
-    "nasr_set_cond", "nasr_forward", "nasr_forward_profiled", "nasr_forward_host", "nasr_stream_reset",
+    "nasr_set_cond", "nasr_forward", "nasr_forward_profiled", "nasr_saturated", "nasr_forward_host", "nasr_stream_reset",
     "nasr_forward_chunk", "nasr_block_forward", "nasr_workspace_bytes",
     "nasr_receptive_field", "nasr_launch_count", "nasr_block_path", "nasr_version",
 )
@@ -64,6 +64,8 @@ def load_library():
     lib.nasr_forward.argtypes = [vp, f32p, f32p, i32, i64, vp]
     lib.nasr_forward_profiled.restype = i32
     lib.nasr_forward_profiled.argtypes = [vp, f32p, f32p, i32, i64, vp, C.c_void_p]
+    lib.nasr_saturated.restype = i32
+    lib.nasr_saturated.argtypes = [vp, vp]
     lib.nasr_forward_host.restype = i32
     lib.nasr_forward_host.argtypes = [vp, f32p, f32p, f32p, i32, i64, vp]
     lib.nasr_stream_reset.restype = i32
@@ -150,6 +152,12 @@ class Engine:
         self._ck(self._lib.nasr_forward_profiled(self._h, x_ptr, y_ptr, B, T, stream or None, ms),
                  "nasr_forward_profiled")
         return list(ms)
+
+    def saturated(self, stream: int = 0) -> bool:
+        rc = self._lib.nasr_saturated(self._h, stream or None)
+        if rc < 0:
+            _raise(self._lib, self._h, rc, "nasr_saturated")
+        return bool(rc)
 
     def forward_host(self, x_ptr: int, cond_ptr: int, y_ptr: int, B: int, T: int, stream: int = 0):
         self._ck(self._lib.nasr_forward_host(self._h, x_ptr, cond_ptr or None, y_ptr, B, T, stream or None),

@@ -44,6 +44,7 @@ struct BlockArgs {
   const float* wout;       // [out_ch][Coutp] (FMT_FINAL)
   int out_ch;
   int final_tanh;
+  unsigned int* sat_flag;  // set to 1 when a value written as SPLIT16 had to be clamped to +-65504
 };
 
 cudaError_t launch_generic_block(const BlockArgs& a, int sm_count, cudaStream_t s);

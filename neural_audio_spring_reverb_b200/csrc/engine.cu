@@ -49,6 +49,8 @@ struct nasr_engine {
   FoldArgs* fold_dev = nullptr;
   int condCap = 0, condB = 0;
   bool fold_valid = false;
+  unsigned int* sat_flag = nullptr;   // device: a SPLIT16 write saturated during the last forward
+  unsigned int* sat_host = nullptr;   // pinned mirror
   DevBuf plane[2];
   // streaming
   int streamB = 0;
@@ -60,6 +62,7 @@ struct nasr_engine {
   size_t budget_bytes = (size_t)24 << 30;
   mutable std::string err;
   int64_t launches = 0;
+  int64_t sat_fallbacks = 0;
 };
 
 namespace {
@@ -165,9 +168,12 @@ void free_block(BlockState& b) {
   b.w0 = nullptr;
 }
 
-BlockArgs make_args(const nasr_engine* e, int i, int B) {
+// tc = false plans the all-fp32 chain (generic kernels, CL planes) for this call
+BlockArgs make_args(const nasr_engine* e, int i, int B, bool tc = true) {
   const BlockState& bs = e->blocks[i];
+  const int n = (int)e->blocks.size();
   BlockArgs a{};
+  a.sat_flag = e->sat_flag;
   a.B = B;
   a.arch = e->desc.arch;
   a.Cin = bs.Cin; a.Cinp = bs.Cinp; a.W = bs.W; a.Wp = bs.Wp; a.Cout = bs.Cout; a.Coutp = bs.Coutp;
@@ -176,13 +182,17 @@ BlockArgs make_args(const nasr_engine* e, int i, int B) {
   a.slope = bs.slope;
   a.wout = e->wout; a.out_ch = e->desc.out_ch; a.final_tanh = e->desc.final_tanh;
   a.in_fmt = bs.in_fmt; a.out_fmt = bs.out_fmt;
+  if (!tc) {
+    a.in_fmt = (i == 0) ? FMT_NCT : FMT_CL;
+    a.out_fmt = (i == n - 1) ? FMT_FINAL : FMT_CL;
+  }
   return a;
 }
 
-int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool allow_tc = true) {
+int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool allow_tc = true, bool tc_chain = true) {
   const BlockState& bs = e->blocks[i];
   cudaError_t err;
-  if (allow_tc && bs.path == 1) {
+  if (allow_tc && tc_chain && bs.path == 1) {
     TcLaunch L{};
     L.cache = &e->tc_cache[i];
     L.in = a.in; L.in_rows = a.in_rows; L.in_clip_stride_elems = a.in_clip_stride;
@@ -191,7 +201,7 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
     t.out = a.out; t.out_fmt = a.out_fmt; t.out_clip_stride = a.out_clip_stride; t.out_rows = a.out_rows;
     t.out_row0 = a.out_row0; t.in_row0 = a.in_row0; t.B = a.B; t.T = a.T; t.k = a.k; t.d = a.d;
     t.scale = a.scale; t.shift = a.shift; t.slope = a.slope; t.inv_sw = bs.inv_sw; t.inv_sr = bs.inv_sr;
-    t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh;
+    t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_flag;
     err = launch_tc_block(L, s);
   } else {
     err = cudaErrorNotSupported;
@@ -231,6 +241,8 @@ void nasr_engine_destroy(nasr_engine* e) {
     for (auto& b : e->blocks) free_block(b);
     if (e->wout) cudaFree(e->wout);
     if (e->fold_dev) cudaFree(e->fold_dev);
+    if (e->sat_flag) cudaFree(e->sat_flag);
+    if (e->sat_host) cudaFreeHost(e->sat_host);
     release(e->plane[0]); release(e->plane[1]);
     for (auto& p : e->splane) release(p);
     release(e->scratch); release(e->hx); release(e->hy); release(e->hc);
@@ -369,7 +381,11 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
   }
   if (rc == NASR_OK) {
     cudaError_t err = cudaMalloc((void**)&e->fold_dev, sizeof(FoldArgs) * n);
-    if (err != cudaSuccess) rc = fail(nullptr, NASR_ERR_NOMEM, "fold args allocation failed");
+    if (err == cudaSuccess) err = cudaMalloc((void**)&e->sat_flag, sizeof(unsigned int));
+    if (err == cudaSuccess) err = cudaMemset(e->sat_flag, 0, sizeof(unsigned int));
+    if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->sat_host, sizeof(unsigned int), cudaHostAllocDefault);
+    if (err != cudaSuccess) rc = fail(nullptr, NASR_ERR_NOMEM, "fold args / flag allocation failed");
+    else *e->sat_host = 0;
   }
   if (rc != NASR_OK) {
     std::string keep = g_create_error;
@@ -426,13 +442,13 @@ int nasr_set_cond(nasr_engine* e, const float* cond_dev, int B, void* stream) {
 }
 
 static int forward_slice(nasr_engine* e, const float* x, float* y, int b0, int B, int64_t T, cudaStream_t s,
-                         cudaEvent_t* ev = nullptr) {
+                         cudaEvent_t* ev = nullptr, bool tc = true) {
   const int n = (int)e->blocks.size();
   const size_t row_bytes = plane_row_bytes(e);
   const long long plane_elems = (long long)T * e->Cp;  // fp32 elements per clip
   for (int i = 0; i < n; ++i) {
     const BlockState& bs = e->blocks[i];
-    BlockArgs a = make_args(e, i, B);
+    BlockArgs a = make_args(e, i, B, tc);
     a.T = T;
     a.scale = bs.scale + (size_t)b0 * bs.Wp;
     a.shift = bs.shift + (size_t)b0 * bs.Wp;
@@ -440,18 +456,18 @@ static int forward_slice(nasr_engine* e, const float* x, float* y, int b0, int B
       a.in = x; a.in_clip_stride = (long long)e->desc.in_ch * T; a.in_rows = T; a.in_row0 = 0;
     } else {
       a.in = e->plane[(i - 1) & 1].p;
-      a.in_clip_stride = (bs.in_fmt == FMT_SPLIT16) ? plane_elems * 2 : plane_elems;
+      a.in_clip_stride = (a.in_fmt == FMT_SPLIT16) ? plane_elems * 2 : plane_elems;
       a.in_rows = T; a.in_row0 = 0;
     }
     if (i == n - 1) {
       a.out = y; a.out_clip_stride = (long long)e->desc.out_ch * T; a.out_rows = T; a.out_row0 = 0;
     } else {
       a.out = e->plane[i & 1].p;
-      a.out_clip_stride = (bs.out_fmt == FMT_SPLIT16) ? plane_elems * 2 : plane_elems;
+      a.out_clip_stride = (a.out_fmt == FMT_SPLIT16) ? plane_elems * 2 : plane_elems;
       a.out_rows = T; a.out_row0 = 0;
     }
     if (ev) cudaEventRecord(ev[i], s);
-    int rc = launch_block(e, a, i, s);
+    int rc = launch_block(e, a, i, s, /*allow_tc=*/true, /*tc_chain=*/tc);
     if (rc != NASR_OK) return rc;
   }
   if (ev) cudaEventRecord(ev[n], s);
@@ -460,10 +476,19 @@ static int forward_slice(nasr_engine* e, const float* x, float* y, int b0, int B
 }
 
 static int forward_impl(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T, void* stream,
-                        float* block_ms);
+                        float* block_ms, bool tc = true);
 
 int nasr_forward(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T, void* stream) {
   return forward_impl(e, x_dev, y_dev, B, T, stream, nullptr);
+}
+
+int nasr_saturated(nasr_engine* e, void* stream) {
+  if (!e) return NASR_ERR_INVALID;
+  DeviceGuard guard(e->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  NASR_CUDA(e, cudaMemcpyAsync(e->sat_host, e->sat_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+  NASR_CUDA(e, cudaStreamSynchronize(s));
+  return *e->sat_host ? 1 : 0;
 }
 
 int nasr_forward_profiled(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T, void* stream,
@@ -473,7 +498,7 @@ int nasr_forward_profiled(nasr_engine* e, const float* x_dev, float* y_dev, int 
 }
 
 static int forward_impl(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T, void* stream,
-                        float* block_ms) {
+                        float* block_ms, bool tc) {
   if (!e) return NASR_ERR_INVALID;
   if (!x_dev || !y_dev) return fail(e, NASR_ERR_INVALID, "x or y is NULL");
   if (B < 1 || T < 0) return fail(e, NASR_ERR_INVALID, "B must be >= 1 and T >= 0");
@@ -505,6 +530,7 @@ static int forward_impl(nasr_engine* e, const float* x_dev, float* y_dev, int B,
       }
     }
   }
+  NASR_CUDA(e, cudaMemsetAsync(e->sat_flag, 0, sizeof(unsigned int), s));
   std::vector<cudaEvent_t> ev;
   if (block_ms) {
     ev.resize(n + 1);
@@ -515,7 +541,7 @@ static int forward_impl(nasr_engine* e, const float* x_dev, float* y_dev, int B,
   for (int b0 = 0; b0 < B && rc == NASR_OK; b0 += slice) {
     const int nb = (B - b0 < slice) ? B - b0 : slice;
     rc = forward_slice(e, x_dev + (size_t)b0 * e->desc.in_ch * T, y_dev + (size_t)b0 * e->desc.out_ch * T, b0, nb, T, s,
-                       block_ms ? ev.data() : nullptr);
+                       block_ms ? ev.data() : nullptr, tc);
     if (block_ms && rc == NASR_OK) {
       if (cudaEventSynchronize(ev[n]) != cudaSuccess) rc = fail(e, NASR_ERR_CUDA, "event synchronize failed");
       for (int i = 0; i < n && rc == NASR_OK; ++i) {
@@ -555,8 +581,18 @@ int nasr_forward_host(nasr_engine* e, const float* x_host, const float* cond_hos
   if (rc != NASR_OK) return rc;
   rc = nasr_forward(e, (const float*)e->hx.p, (float*)e->hy.p, B, T, stream);
   if (rc != NASR_OK) return rc;
+  NASR_CUDA(e, cudaMemcpyAsync(e->sat_host, e->sat_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
   NASR_CUDA(e, cudaMemcpyAsync(y_host, e->hy.p, yb, cudaMemcpyDeviceToHost, s));
   NASR_CUDA(e, cudaStreamSynchronize(s));
+  if (*e->sat_host) {
+    // an activation exceeded the fp16 range of the SPLIT16 planes: redo this call on the fp32 kernels
+    e->sat_fallbacks += 1;
+    rc = forward_impl(e, (const float*)e->hx.p, (float*)e->hy.p, B, T, stream, nullptr, /*tc=*/false);
+    if (rc != NASR_OK) return rc;
+    NASR_CUDA(e, cudaMemcpyAsync(y_host, e->hy.p, yb, cudaMemcpyDeviceToHost, s));
+    NASR_CUDA(e, cudaStreamSynchronize(s));
+    *e->sat_host = 1;
+  }
   return NASR_OK;
 }
 
@@ -613,6 +649,7 @@ int nasr_stream_reset(nasr_engine* e, int B, void* stream) {
   if (B < 1) return fail(e, NASR_ERR_INVALID, "B must be >= 1");
   DeviceGuard guard(e->device);
   cudaStream_t s = (cudaStream_t)stream;
+  NASR_CUDA(e, cudaMemsetAsync(e->sat_flag, 0, sizeof(unsigned int), s));
   const long long Tcap = (e->streamB == B && e->streamTcap > 0) ? e->streamTcap : 1024;
   if (e->streamB == B && !e->splane.empty()) {
     for (auto& q : e->splane) NASR_CUDA(e, cudaMemsetAsync(q.p, 0, q.cap, s));

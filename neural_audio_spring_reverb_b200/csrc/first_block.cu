@@ -89,6 +89,10 @@ __global__ void __launch_bounds__(FB_ROWS, 2) first_block_kernel(const BlockArgs
       if (a.out_fmt == FMT_SPLIT16) {
         __half* dst = (__half*)a.out + (long long)b * a.out_clip_stride + (a.out_row0 + t) * (2LL * a.Coutp);
         uint32_t hi[C / 2], lo[C / 2];
+        float vmax = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) vmax = fmaxf(vmax, fabsf(o[c]));
+        if (vmax > 65504.f) *a.sat_flag = 1u;
 #pragma unroll
         for (int c = 0; c < C; c += 2) {
           const float x0 = fminf(fmaxf(o[c], -65504.f), 65504.f), x1 = fminf(fmaxf(o[c + 1], -65504.f), 65504.f);

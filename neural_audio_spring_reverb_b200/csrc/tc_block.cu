@@ -410,6 +410,10 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
             uint4* dst = reinterpret_cast<uint4*>((__half*)a.out + (long long)s.b * a.out_clip_stride +
                                                   (a.out_row0 + t) * (2LL * C));
             uint32_t hi[16], lo[16];
+            float vmax = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) vmax = fmaxf(vmax, fabsf(o[c]));
+            if (vmax > 65504.f) *a.sat_flag = 1u;
 #pragma unroll
             for (int c = 0; c < C; c += 2) {
               const float x0 = fminf(fmaxf(o[c], -65504.f), 65504.f), x1 = fminf(fmaxf(o[c + 1], -65504.f), 65504.f);

@@ -31,6 +31,7 @@ struct TcArgs {
   float slope, inv_sw, inv_sr;
   const float* wout;    // [out_ch][32]
   int out_ch, final_tanh;
+  unsigned int* sat_flag;   // set when a SPLIT16 output had to be clamped to +-65504
   int dbg;           // dev only (NASR_TC_DBG): 1 = issue no MMAs, 2 = epilogue skips math + stores
 };
 

@@ -185,6 +185,14 @@ class FusedNetMixin:
         eng.forward_host(xc.data_ptr(), cptr, y.data_ptr(), B, T, stream)
         return y
 
+    def saturated(self) -> bool:
+        """True if the last device-tensor forward had to clamp an activation to the fp16 range of
+        the tensor-core path (|a| > 65504): its result is then not trustworthy - run with
+        NASR_PATH=fp32. (Host-tensor forwards detect this themselves and fall back.) Synchronises."""
+        eng = self._engine()
+        dev = torch.device("cuda", eng.device)
+        return eng.saturated(torch.cuda.current_stream(dev).cuda_stream)
+
     # ---- streaming (reference wrapper.py:14-57 semantics) ------------------
     def reset_stream(self, batch_size: int = 1) -> None:
         """Zero the per-block input history, like freshly built PaddingCached buffers."""

@@ -195,3 +195,42 @@ def test_make_inference_and_rtf_plumbing(tmp_path):
     from neural_audio_spring_reverb_b200.rtf import measure_rtf
     out = measure_rtf(types.SimpleNamespace(checkpoint=str(ck), device=torch.device(DEV), audio_dir=str(tmp_path)))
     assert tuple(out.shape) == (1, 48000)
+
+
+def test_fp16_range_guard_falls_back_to_fp32_kernels():
+    """Activations beyond +-65504 do not fit the SPLIT16 planes of the tensor-core path: the
+    host-tensor forward detects the clamp and redoes the call on the fp32 kernels; the
+    device-tensor forward reports it through saturated()."""
+    cfg = O.CONFIGS["cfg2"]
+    sd = O.config_state("cfg2")
+    m = build_model(cfg, sd, DEV)
+    x = O.make_input(1, 1, 20000) * 1.0e8               # inter-block activations far beyond 65504
+    cond = torch.tensor([[0.5, 0.5]])
+    ref = O.forward(sd, O.config_dilations(cfg), x, cond)
+    y_host = m(x, cond)                                # host path: automatic fallback
+    assert rel_err(y_host, ref) <= REL_TOL
+    y_dev = m(x.to(DEV), cond.to(DEV))                 # device path: flagged, not silently wrong
+    assert m.saturated() is True
+    small = m(O.make_input(1, 1, 20000).to(DEV), cond.to(DEV))
+    assert m.saturated() is False and torch.isfinite(small).all() and torch.isfinite(y_dev).all()
+
+
+def test_cfg5_long_stream_chunked_equals_oneshot_and_cpu_prefix():
+    """BASELINE cfg5 (streaming, 65 536-sample chunks, per-block history carried): GPU chunked ==
+    GPU one-shot on a 5-minute prefix, and the first 30 s against the CPU oracle."""
+    import neural_audio_spring_reverb_b200 as N
+    cfg = O.CONFIGS["cfg2"]
+    sd = O.config_state("cfg2")
+    m = build_model(cfg, sd, DEV)
+    T = 5 * 60 * 48000
+    g = torch.Generator(device=DEV).manual_seed(7)
+    x = torch.rand((1, 1, T), device=DEV, generator=g) * 2 - 1
+    cond = torch.tensor([[0.5, 0.5]], device=DEV)
+    one = m(x, cond)
+    st = N.CachedStream(m)
+    got = torch.cat([st(x[..., s:s + 65536], cond) for s in range(0, T, 65536)], -1)
+    assert rel_err(got, one) <= 1e-6
+    Tp = 30 * 48000
+    ref = O.forward(sd, O.config_dilations(cfg), x[..., :Tp].cpu(), cond.cpu())
+    assert rel_err(got[..., :Tp], ref) <= REL_TOL
+    assert m.saturated() is False
