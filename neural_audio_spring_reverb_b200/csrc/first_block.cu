@@ -9,10 +9,14 @@
 
 namespace nasr {
 
-constexpr int FB_ROWS = 256;   // samples per CTA tile = threads per CTA
+constexpr int FB_ROWS = 256;      // samples per CTA tile
+constexpr int FB_THREADS = 128;   // each thread owns rows r and r + 128 of the tile
+
+// packed fp32x2 FMA (sm_100): halves the FMA instruction count of this issue-bound kernel
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
 template <int ARCH, int C>
-__global__ void __launch_bounds__(FB_ROWS, 2) first_block_kernel(const BlockArgs a, const float* __restrict__ w0) {
+__global__ void __launch_bounds__(FB_THREADS, ((ARCH == 1 ? 2 * C : C) > 32 ? 2 : 3)) first_block_kernel(const BlockArgs a, const float* __restrict__ w0) {
   constexpr int W = ARCH == 1 ? 2 * C : C;
   extern __shared__ __align__(16) float fsm[];
   const int Cin = a.Cin, k = a.k, d = a.d;
@@ -20,106 +24,125 @@ __global__ void __launch_bounds__(FB_ROWS, 2) first_block_kernel(const BlockArgs
   float* ws = fsm;                         // [k][Cin][W]   original channel order
   float* rs = ws + k * Cin * W;            // [Cin][C]
   float* os = rs + Cin * C;                // [out_ch][C]   (FMT_FINAL)
-  float* xs = os + (a.out_fmt == FMT_FINAL ? a.out_ch * C : 0);   // [Cin][H + FB_ROWS]
+  float* ss = os + (a.out_fmt == FMT_FINAL ? a.out_ch * C : 0);   // [2][W] scale, shift of the current clip
+  float* xs = ss + 2 * W;                  // [Cin][H + FB_ROWS]
   const int XW = H + FB_ROWS;
 
-  for (int i = threadIdx.x; i < k * Cin * W; i += FB_ROWS) ws[i] = w0[i];
-  for (int i = threadIdx.x; i < Cin * C; i += FB_ROWS) {
+  for (int i = threadIdx.x; i < k * Cin * W; i += FB_THREADS) ws[i] = w0[i];
+  for (int i = threadIdx.x; i < Cin * C; i += FB_THREADS) {
     const int ci = i / C, c = i - ci * C;
     rs[i] = a.wres[ci * a.Coutp + c];
   }
   if (a.out_fmt == FMT_FINAL)
-    for (int i = threadIdx.x; i < a.out_ch * C; i += FB_ROWS) os[i] = a.wout[(i / C) * a.Coutp + (i % C)];
+    for (int i = threadIdx.x; i < a.out_ch * C; i += FB_THREADS) os[i] = a.wout[(i / C) * a.Coutp + (i % C)];
 
   const long long tiles_per_clip = (a.T + FB_ROWS - 1) / FB_ROWS;
   const long long ntiles = tiles_per_clip * a.B;
+  int cur_b = -1;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int b = (int)(tile / tiles_per_clip);
     const long long t0 = (tile - (long long)b * tiles_per_clip) * FB_ROWS;
     __syncthreads();   // previous tile's readers are done (also orders the weight fill)
     const float* src = (const float*)a.in + (long long)b * a.in_clip_stride;
-    for (int i = threadIdx.x; i < Cin * XW; i += FB_ROWS) {
+    for (int i = threadIdx.x; i < Cin * XW; i += FB_THREADS) {
       const int ci = i / XW, p = i - ci * XW;
       const long long t = t0 - H + p, row = a.in_row0 + t;
       xs[i] = (row >= 0 && t < a.T) ? __ldg(src + (long long)ci * a.in_rows + row) : 0.f;
     }
+    if (b != cur_b) {   // folded scale/shift of this clip, [tanh | sigmoid] halves each Coutp wide for GCN
+      cur_b = b;
+      for (int i = threadIdx.x; i < W; i += FB_THREADS) {
+        const int src_i = (ARCH == 1 && i >= C) ? a.Coutp + (i - C) : i;
+        ss[i] = __ldg(a.scale + (long long)b * a.Wp + src_i);
+        ss[W + i] = __ldg(a.shift + (long long)b * a.Wp + src_i);
+      }
+    }
     __syncthreads();
 
     const int r = threadIdx.x;
-    const long long t = t0 + r;
-    float acc[W];
+    float2 acc0[W / 2], acc1[W / 2];   // rows r and r + 128
 #pragma unroll
-    for (int n = 0; n < W; ++n) acc[n] = 0.f;
+    for (int n = 0; n < W / 2; ++n) acc0[n] = acc1[n] = make_float2(0.f, 0.f);
     for (int j = 0; j < k; ++j)
       for (int ci = 0; ci < Cin; ++ci) {
-        const float xv = xs[ci * XW + r + j * d];
+        const float x0 = xs[ci * XW + r + j * d], x1 = xs[ci * XW + r + 128 + j * d];
+        const float2 xa = make_float2(x0, x0), xb = make_float2(x1, x1);
         const float4* wv = reinterpret_cast<const float4*>(ws + (j * Cin + ci) * W);
 #pragma unroll
         for (int n = 0; n < W / 4; ++n) {
           const float4 q = wv[n];
-          acc[4 * n] = fmaf(xv, q.x, acc[4 * n]);
-          acc[4 * n + 1] = fmaf(xv, q.y, acc[4 * n + 1]);
-          acc[4 * n + 2] = fmaf(xv, q.z, acc[4 * n + 2]);
-          acc[4 * n + 3] = fmaf(xv, q.w, acc[4 * n + 3]);
+          const float2 qa = make_float2(q.x, q.y), qb = make_float2(q.z, q.w);
+          acc0[2 * n] = fma2(xa, qa, acc0[2 * n]);
+          acc0[2 * n + 1] = fma2(xa, qb, acc0[2 * n + 1]);
+          acc1[2 * n] = fma2(xb, qa, acc1[2 * n]);
+          acc1[2 * n + 1] = fma2(xb, qb, acc1[2 * n + 1]);
         }
       }
-    const float* sc = a.scale + (long long)b * a.Wp;
-    const float* sh = a.shift + (long long)b * a.Wp;
-    float o[C];
-    if (ARCH == 0) {
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float y = fmaf(acc[c], __ldg(sc + c), __ldg(sh + c));
-        o[c] = y > 0.f ? y : a.slope * y;
-      }
-    } else {
+    for (int half = 0; half < 2; ++half) {
+      const float2* acc = half ? acc1 : acc0;
+      const int rr = r + 128 * half;
+      const long long t = t0 + rr;
+      float o[C];
+      const float2* sc2 = reinterpret_cast<const float2*>(ss);
+      const float2* sh2 = reinterpret_cast<const float2*>(ss + W);
+      if (ARCH == 0) {
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float yt = fmaf(acc[c], __ldg(sc + c), __ldg(sh + c));
-        const float ys = fmaf(acc[C + c], __ldg(sc + a.Coutp + c), __ldg(sh + a.Coutp + c));
-        o[c] = tanhf(yt) * (1.0f / (1.0f + expf(-ys)));
-      }
-    }
-    for (int ci = 0; ci < Cin; ++ci) {
-      const float xv = xs[ci * XW + r + H];
-#pragma unroll
-      for (int c = 0; c < C; ++c) o[c] = fmaf(xv, rs[ci * C + c], o[c]);
-    }
-    if (t < a.T) {
-      if (a.out_fmt == FMT_SPLIT16) {
-        __half* dst = (__half*)a.out + (long long)b * a.out_clip_stride + (a.out_row0 + t) * (2LL * a.Coutp);
-        uint32_t hi[C / 2], lo[C / 2];
-        float vmax = 0.f;
-#pragma unroll
-        for (int c = 0; c < C; ++c) vmax = fmaxf(vmax, fabsf(o[c]));
-        if (vmax > 65504.f) *a.sat_flag = 1u;
-#pragma unroll
-        for (int c = 0; c < C; c += 2) {
-          const float x0 = fminf(fmaxf(o[c], -65504.f), 65504.f), x1 = fminf(fmaxf(o[c + 1], -65504.f), 65504.f);
-          const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-          const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-          hi[c >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-          lo[c >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        for (int c = 0; c < C / 2; ++c) {
+          const float2 y = fma2(acc[c], sc2[c], sh2[c]);
+          o[2 * c] = y.x > 0.f ? y.x : a.slope * y.x;
+          o[2 * c + 1] = y.y > 0.f ? y.y : a.slope * y.y;
         }
-        uint4* d4 = reinterpret_cast<uint4*>(dst);
-        uint4* l4 = reinterpret_cast<uint4*>(dst + a.Coutp);
+      } else {
 #pragma unroll
-        for (int v = 0; v < C / 8; ++v) {
-          d4[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-          l4[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+        for (int c = 0; c < C / 2; ++c) {
+          const float2 yt = fma2(acc[c], sc2[c], sh2[c]);
+          const float2 ys = fma2(acc[C / 2 + c], sc2[C / 2 + c], sh2[C / 2 + c]);
+          o[2 * c] = tanhf(yt.x) * (1.0f / (1.0f + expf(-ys.x)));
+          o[2 * c + 1] = tanhf(yt.y) * (1.0f / (1.0f + expf(-ys.y)));
         }
-      } else if (a.out_fmt == FMT_CL) {
-        float4* dst = reinterpret_cast<float4*>((float*)a.out + (long long)b * a.out_clip_stride +
-                                                (a.out_row0 + t) * (long long)a.Coutp);
+      }
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float xv = xs[ci * XW + rr + H];
 #pragma unroll
-        for (int v = 0; v < C / 4; ++v) dst[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
-      } else {  // FMT_FINAL
-        for (int oc = 0; oc < a.out_ch; ++oc) {
-          float y = 0.f;
+        for (int c = 0; c < C; ++c) o[c] = fmaf(xv, rs[ci * C + c], o[c]);
+      }
+      if (t < a.T) {
+        if (a.out_fmt == FMT_SPLIT16) {
+          __half* dst = (__half*)a.out + (long long)b * a.out_clip_stride + (a.out_row0 + t) * (2LL * a.Coutp);
+          uint32_t hi[C / 2], lo[C / 2];
+          float vmax = 0.f;
 #pragma unroll
-          for (int c = 0; c < C; ++c) y = fmaf(o[c], os[oc * C + c], y);
-          if (a.final_tanh) y = tanhf(y);
-          ((float*)a.out)[(long long)b * a.out_clip_stride + (long long)oc * a.out_rows + a.out_row0 + t] = y;
+          for (int c = 0; c < C; ++c) vmax = fmaxf(vmax, fabsf(o[c]));
+          if (vmax > 65504.f) *a.sat_flag = 1u;
+#pragma unroll
+          for (int c = 0; c < C; c += 2) {
+            const float x0 = fminf(fmaxf(o[c], -65504.f), 65504.f), x1 = fminf(fmaxf(o[c + 1], -65504.f), 65504.f);
+            const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+            const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+            hi[c >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            lo[c >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+          }
+          uint4* d4 = reinterpret_cast<uint4*>(dst);
+          uint4* l4 = reinterpret_cast<uint4*>(dst + a.Coutp);
+#pragma unroll
+          for (int v = 0; v < C / 8; ++v) {
+            d4[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+            l4[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+          }
+        } else if (a.out_fmt == FMT_CL) {
+          float4* dst = reinterpret_cast<float4*>((float*)a.out + (long long)b * a.out_clip_stride +
+                                                  (a.out_row0 + t) * (long long)a.Coutp);
+#pragma unroll
+          for (int v = 0; v < C / 4; ++v) dst[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+        } else {  // FMT_FINAL
+          for (int oc = 0; oc < a.out_ch; ++oc) {
+            float y = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) y = fmaf(o[c], os[oc * C + c], y);
+            if (a.final_tanh) y = tanhf(y);
+            ((float*)a.out)[(long long)b * a.out_clip_stride + (long long)oc * a.out_rows + a.out_row0 + t] = y;
+          }
         }
       }
     }
@@ -131,7 +154,8 @@ static cudaError_t launch_fb(const BlockArgs& a, const float* w0, int sm_count, 
   constexpr int W = ARCH == 1 ? 2 * C : C;
   const int H = (a.k - 1) * a.d;
   const size_t smem = sizeof(float) * ((size_t)a.k * a.Cin * W + (size_t)a.Cin * C +
-                                       (a.out_fmt == FMT_FINAL ? (size_t)a.out_ch * C : 0) + (size_t)a.Cin * (H + FB_ROWS));
+                                       (a.out_fmt == FMT_FINAL ? (size_t)a.out_ch * C : 0) + 2 * (size_t)W +
+                                       (size_t)a.Cin * (H + FB_ROWS));
   if (smem > 100 * 1024) return cudaErrorNotSupported;
   auto kern = first_block_kernel<ARCH, C>;
   static size_t configured = 0;
@@ -141,9 +165,9 @@ static cudaError_t launch_fb(const BlockArgs& a, const float* w0, int sm_count, 
     configured = smem;
   }
   const long long ntiles = ((a.T + FB_ROWS - 1) / FB_ROWS) * a.B;
-  long long grid = (long long)sm_count * 4;
+  long long grid = (long long)sm_count * 8;
   if (grid > ntiles) grid = ntiles;
-  kern<<<(unsigned)grid, FB_ROWS, smem, s>>>(a, w0);
+  kern<<<(unsigned)grid, FB_THREADS, smem, s>>>(a, w0);
   return cudaGetLastError();
 }
 
