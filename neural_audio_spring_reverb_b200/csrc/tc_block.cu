@@ -41,6 +41,9 @@
 #ifndef TC_NW_GCN
 #define TC_NW_GCN 3
 #endif
+#ifndef TC_ES_TCN
+#define TC_ES_TCN 1
+#endif
 
 namespace nasr {
 using namespace sm100;
@@ -131,7 +134,7 @@ struct Sched {
 // q % ESETS == e), then 1 TMA producer warp, then NW MMA issuer warps (tile q -> issuer q % NW).
 // TCN is issue-bound (N = 32/64 instructions), GCN epilogue-bound (tanh, sigmoid per element).
 template <int ARCH> struct TcCfg;
-template <> struct TcCfg<0> { static constexpr int ESETS = 1, NW = TC_NW_TCN; };
+template <> struct TcCfg<0> { static constexpr int ESETS = TC_ES_TCN, NW = TC_NW_TCN; };
 template <> struct TcCfg<1> { static constexpr int ESETS = 2, NW = TC_NW_GCN; };
 template <int ARCH> constexpr int tc_threads() { return (4 * TcCfg<ARCH>::ESETS + 1 + TcCfg<ARCH>::NW) * 32; }
 

@@ -54,14 +54,18 @@ class FusedNetMixin:
         return self.kernel_size + (self.kernel_size - 1) * sum(self.dilations[1:])
 
     # ---- engine life cycle -------------------------------------------------
+    def _nasr_layers(self):
+        """The fused layers in execution order (TCN/GCN: the blocks; WaveNet flattens its stacks)."""
+        return list(self.blocks)
+
     def _nasr_has_film(self) -> bool:
-        return hasattr(self.blocks[0], "film")
+        return hasattr(self._nasr_layers()[0], "film")
 
     def _nasr_tensors(self) -> List[Tensor]:
         """Parameters/buffers in the order nasr_weight_count() documents."""
         out: List[Tensor] = []
         film = self._nasr_has_film()
-        for blk in self.blocks:
+        for blk in self._nasr_layers():
             out += [blk.conv.conv.weight, blk.conv.conv.bias]
             if film:
                 out += [blk.film.adaptor.weight, blk.film.adaptor.bias, blk.film.bn.weight,
@@ -111,12 +115,13 @@ class FusedNetMixin:
         if old is not None:
             old[2].close()
         blob = self.weight_blob().numpy()
+        layers = self._nasr_layers()
         eng = _native.Engine(
-            arch=self._nasr_arch, n_blocks=self.n_blocks, in_ch=self.in_ch, out_ch=self.out_ch,
-            n_channels=self.channels[0], kernel_size=self.kernel_size, cond_dim=self.cond_dim,
+            arch=self._nasr_arch, n_blocks=len(layers), in_ch=self.in_ch, out_ch=self.out_ch,
+            n_channels=layers[0].out_ch, kernel_size=self.kernel_size, cond_dim=self.cond_dim,
             has_film=self._nasr_has_film(), final_tanh=self._nasr_final_tanh,
-            dilations=self.dilations, weights=blob, device=index, path=_path_from_env(),
-            bn_eps=float(self.blocks[0].film.bn.eps) if self._nasr_has_film() else 1e-5)
+            dilations=[l.dilation for l in layers], weights=blob, device=index, path=_path_from_env(),
+            bn_eps=float(layers[0].film.bn.eps) if self._nasr_has_film() else 1e-5)
         stamp = sum(t._version for t in tensors) + tensors[0].data_ptr()
         self.__dict__["_nasr_cache"] = (tensors, stamp, eng)
         self.__dict__["_nasr_stream_B"] = None
@@ -214,7 +219,7 @@ class FusedNetMixin:
             raise RuntimeError("inference-only: call .eval()")
         eng = self._engine()
         dev = torch.device("cuda", eng.device)
-        blk = self.blocks[index]
+        blk = self._nasr_layers()[index]
         assert x.ndim == 3 and x.shape[1] == blk.in_ch
         B, _, T = x.shape
         xc = x.detach().to(dev, torch.float32).contiguous()

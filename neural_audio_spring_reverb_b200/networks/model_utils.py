@@ -9,13 +9,16 @@ import yaml
 
 from .gcn import GCN
 from .tcn import TCN
+from .wavenet import WaveNet
 
 # constructor keyword allow-lists (model_utils.py:50-99)
 _CTOR_KEYS = {
     "TCN": (TCN, {"n_channels", "n_layers", "dilation_growth", "in_ch", "out_ch", "kernel_size", "cond_dim"}),
     "GCN": (GCN, {"in_ch", "out_ch", "n_blocks", "n_channels", "dilation_growth", "kernel_size", "cond_dim"}),
+    "WaveNet": (WaveNet, {"in_ch", "out_ch", "n_blocks", "n_stacks", "n_channels", "kernel_size", "dilation_growth",
+                          "cond_dim"}),
 }
-_OUT_OF_SCOPE = {"LSTM", "GRU", "WaveNet"}
+_OUT_OF_SCOPE = {"LSTM", "GRU"}
 
 
 def parse_config(config_path):
@@ -30,7 +33,7 @@ def initialize_model(device, config):
     kind = config["model_type"]
     if kind in _OUT_OF_SCOPE:
         raise NotImplementedError(
-            f"model_type {kind!r} is not on the B200 inference path (TCN and GCN only)")
+            f"model_type {kind!r} is not on the B200 inference path (TCN, GCN and WaveNet only)")
     if kind not in _CTOR_KEYS:
         raise ValueError(f"Unknown model type: {kind}")
     cls, allowed = _CTOR_KEYS[kind]

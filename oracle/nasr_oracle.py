@@ -83,6 +83,24 @@ def gcn_block(x: Tensor, cond: Tensor, sd: StateDict, i: int, dilation: int,
     return y + F.conv1d(x, sd[p + "res.weight"])
 
 
+def flatten_wavenet_state(sd: StateDict) -> StateDict:
+    """networks/wavenet.py:11-60,94-116: a WaveNet is n_blocks x n_stacks `Conv1dStack`s whose
+    forward (wavenet.py:53-60) is line for line GCNBlock.forward (gcn.py:53-61); renaming
+    blocks.b.stacks.s.* to blocks.(b*n_stacks+s).* lets the GCN restatement above run it.
+    The caller passes the flat dilation list [g**s for each block for each stack]."""
+    if not any(".stacks." in k for k in sd):
+        return sd
+    n_stacks = 1 + max(int(k.split(".")[3]) for k in sd if ".stacks." in k)
+    out: StateDict = {}
+    for k, v in sd.items():
+        parts = k.split(".")
+        if len(parts) > 3 and parts[0] == "blocks" and parts[2] == "stacks":
+            out[".".join(["blocks", str(int(parts[1]) * n_stacks + int(parts[3]))] + parts[4:])] = v
+        else:
+            out[k] = v
+    return out
+
+
 def n_blocks_of(sd: StateDict) -> int:
     return 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("blocks."))
 
@@ -101,7 +119,7 @@ def forward(sd: StateDict, dilations: Sequence[int], x: Tensor, cond: Optional[T
             dtype: torch.dtype = torch.float32) -> Tensor:
     """networks/tcn.py:150-155 (TCN.forward) / networks/gcn.py:140-147 (GCN.forward):
     blocks in sequence, out_net 1x1, tanh for GCN only."""
-    sd = {k: v.to(dtype) for k, v in sd.items() if v.is_floating_point()}
+    sd = {k: v.to(dtype) for k, v in flatten_wavenet_state(sd).items() if v.is_floating_point()}
     x = x.to(dtype)
     cond = None if cond is None else cond.to(dtype)
     gcn = is_gcn(sd)

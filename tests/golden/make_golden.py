@@ -31,6 +31,7 @@ sys.path.insert(0, str(ROOT))
 
 from neural_audio_spring_reverb.networks.tcn import TCN as RefTCN  # noqa: E402
 from neural_audio_spring_reverb.networks.gcn import GCN as RefGCN  # noqa: E402
+from neural_audio_spring_reverb.networks.wavenet import WaveNet as RefWaveNet  # noqa: E402
 from neural_audio_spring_reverb.networks.custom_layers import Conv1dCausal  # noqa: E402
 from oracle import nasr_oracle as O  # noqa: E402
 
@@ -50,6 +51,10 @@ def ref_streaming_namespace():
 
 
 def build_ref(cfg):
+    if cfg["arch"] == "WaveNet":
+        return RefWaveNet(in_ch=cfg.get("in_ch", 1), out_ch=cfg.get("out_ch", 1), n_blocks=cfg["n_blocks"],
+                          n_stacks=cfg["n_stacks"], n_channels=cfg["n_channels"], kernel_size=cfg["kernel_size"],
+                          dilation_growth=cfg["dilation_growth"], cond_dim=cfg["cond_dim"])
     if cfg["arch"] == "TCN":
         return RefTCN(cfg["n_channels"], cfg["n_blocks"], cfg["dilation_growth"], in_ch=cfg.get("in_ch", 1),
                       out_ch=cfg.get("out_ch", 1), kernel_size=cfg["kernel_size"], cond_dim=cfg["cond_dim"])
@@ -77,7 +82,9 @@ def run_case(name, cfg, sd, B, T, cond_vals, store_weights, check_stream=False):
     noise = float((y.double() - y64).abs().max() / y64.abs().max())
     meta = dict(name=name, cfg=cfg, B=B, T=T, cond=cond_vals, weights_checksum=checksum(sd),
                 ref_fp32_vs_fp64=noise, ymax=float(y.abs().max()),
-                dilations=[int(d) for d in model.dilations], rf=int(model.calc_receptive_field()),
+                dilations=([int(d) for d in model.dilations] if hasattr(model, "dilations") else
+                           [int(st.conv.conv.dilation[0]) for blk in model.blocks for st in blk.stacks]),
+                rf=int(model.calc_receptive_field()),
                 params=int(sum(p.numel() for p in model.parameters())))
     if check_stream:
         ns = ref_streaming_namespace()
@@ -110,7 +117,8 @@ def main():
         ("synth_tcn_shipped_shape", "tcn-shipped", 1, 90000, [0.3, 0.7], False),
         ("synth_gcn3_shipped_shape", "gcn3-shipped", 1, 140000, [0.3, 0.7], False),
     ]
-    for name, cname, B, T, cond, stream in synth:
+    only = sys.argv[1] if len(sys.argv) > 1 else None
+    for name, cname, B, T, cond, stream in ([] if only else synth):
         cfg = dict(O.CONFIGS[cname])
         run_case(name, cfg, O.config_state(cname), B, T, cond, store_weights=False, check_stream=stream)
     # odd shapes: no FiLM, multi-channel I/O, channel counts that need padding
@@ -120,7 +128,7 @@ def main():
         ("synth_gcn_c6", dict(arch="GCN", n_blocks=2, n_channels=6, kernel_size=3, dilation_growth=5, cond_dim=1), 3, 2000, [0.6]),
         ("synth_gcn_k99", dict(arch="GCN", n_blocks=2, n_channels=32, kernel_size=99, dilation_growth=16, cond_dim=2), 1, 6000, [0.2, 0.8]),
     ]
-    for name, cfg, B, T, cond in odd:
+    for name, cfg, B, T, cond in ([] if only else odd):
         sd = O.build_state(cfg["arch"], cfg["n_blocks"], cfg["n_channels"], cfg["kernel_size"], cfg["cond_dim"],
                            in_ch=cfg.get("in_ch", 1), out_ch=cfg.get("out_ch", 1), seed=7)
         cfg["seed"] = 7
@@ -136,14 +144,24 @@ def main():
         ("models/GCN-springset-20240324-151439-16kHz.pt", 72000),
         ("models/kernel-99/GCN-99-egfxset-20240310-095201-48kHz.pt", 56000),
         ("models/kernel-99/GCN-99-springset-20240310-141620-16kHz.pt", 16000),
+        # WaveNet: Conv1dStack == GCNBlock, same kernels, restarting dilations
+        ("models/WaveNet-egfxset-20240229-010530-48kHz.pt", 48000),
+        ("models/WaveNet-springset-20240228-145414-16kHz.pt", 46000),
+        ("models/kernel-99/WaveNet-99-egfxset-20240229-214944-48kHz.pt", 8192),
+        ("models/kernel-99/WaveNet-99-springset-20240229-080542-16kHz.pt", 8192),
     ]
+    only = sys.argv[1] if len(sys.argv) > 1 else None
     for rel, T in shipped:
+        if only and only not in rel:
+            continue
         ck = torch.load(REF / rel, map_location="cpu")
         c = ck["config_state_dict"]
         cfg = dict(arch=c["model_type"], n_blocks=c.get("n_layers", c.get("n_blocks")), n_channels=c["n_channels"],
                    kernel_size=c["kernel_size"], dilation_growth=c["dilation_growth"], cond_dim=c["cond_dim"],
                    in_ch=c["in_ch"], out_ch=c["out_ch"], batch_size=c["batch_size"], sample_rate=c["sample_rate"],
                    checkpoint=rel)
+        if c["model_type"] == "WaveNet":
+            cfg["n_stacks"] = c["n_stacks"]
         name = "ckpt_" + Path(rel).stem.replace("-", "_")
         run_case(name, cfg, ck["model_state_dict"], 1, T, [c.get("c0", 0.0), c.get("c1", 0.0)], store_weights=True)
         run_case(name + "_cond", cfg, ck["model_state_dict"], 1, min(T, 20000), [0.35, 0.8], store_weights=False)

@@ -75,7 +75,7 @@ def test_strict_load_of_shipped_checkpoints(name):
         assert tuple(v.shape) == tuple(sd[k].shape), k
     assert m.calc_receptive_field() == meta["rf"]
     assert sum(p.numel() for p in m.parameters()) == meta["params"]
-    assert m.dilations == meta["dilations"]
+    assert [layer.dilation for layer in m._nasr_layers()] == meta["dilations"]
 
 
 def test_reference_attribute_surface():

@@ -48,7 +48,11 @@ def golden_inputs(meta):
 def build_model(cfg, sd, device):
     """Our drop-in module with the reference's constructor arguments."""
     import neural_audio_spring_reverb_b200 as N
-    if cfg["arch"] == "TCN":
+    if cfg["arch"] == "WaveNet":
+        m = N.WaveNet(in_ch=cfg.get("in_ch", 1), out_ch=cfg.get("out_ch", 1), n_blocks=cfg["n_blocks"],
+                      n_stacks=cfg["n_stacks"], n_channels=cfg["n_channels"], kernel_size=cfg["kernel_size"],
+                      dilation_growth=cfg["dilation_growth"], cond_dim=cfg["cond_dim"])
+    elif cfg["arch"] == "TCN":
         m = N.TCN(cfg["n_channels"], cfg["n_blocks"], cfg["dilation_growth"], in_ch=cfg.get("in_ch", 1),
                   out_ch=cfg.get("out_ch", 1), kernel_size=cfg["kernel_size"], cond_dim=cfg["cond_dim"])
     else:
