@@ -234,3 +234,54 @@ def test_cfg5_long_stream_chunked_equals_oneshot_and_cpu_prefix():
     ref = O.forward(sd, O.config_dilations(cfg), x[..., :Tp].cpu(), cond.cpu())
     assert rel_err(got[..., :Tp], ref) <= REL_TOL
     assert m.saturated() is False
+
+
+TC_SHAPES = [
+    # arch, n_blocks, k, growth      (C = 32 -> blocks 1.. take the tcgen05 kernel)
+    ("TCN", 4, 1, 7), ("TCN", 4, 2, 3), ("TCN", 5, 5, 3), ("TCN", 4, 7, 10), ("TCN", 3, 31, 9),
+    ("TCN", 4, 4, 100), ("TCN", 3, 6, 130), ("TCN", 3, 9, 127), ("TCN", 3, 3, 129),
+    ("GCN", 4, 5, 4), ("GCN", 3, 9, 11), ("GCN", 3, 2, 200), ("GCN", 3, 15, 13),
+]
+
+
+@pytest.mark.parametrize("arch,n_blocks,k,g", TC_SHAPES)
+def test_tensor_core_path_shapes(arch, n_blocks, k, g):
+    """Tap counts, odd / non-power-of-two dilations, both walk modes (d < 128 and d >= 128, partial
+    lanes) of the tcgen05 kernel, against the oracle; and the same net streamed in ragged chunks."""
+    import neural_audio_spring_reverb_b200 as N
+    cfg = dict(arch=arch, n_blocks=n_blocks, n_channels=32, kernel_size=k, dilation_growth=g, cond_dim=2)
+    sd = O.build_state(arch, n_blocks, 32, k, 2, seed=k * 31 + g)
+    dil = [g ** i for i in range(n_blocks)]
+    m = build_model(cfg, sd, DEV)
+    assert [m._engine().block_path(i) for i in range(n_blocks)] == [0] + [1] * (n_blocks - 1)
+    rf = O.receptive_field(k, dil) if k > 1 else 1
+    T = min(max(3 * rf, 9000), 60000) + 37
+    x = O.make_input(2, 1, T)
+    cond = torch.tensor([[0.2, 0.9], [0.7, 0.1]])
+    ref = O.forward(sd, dil, x, cond)
+    y = m(x.to(DEV), cond.to(DEV))
+    assert rel_err(y, ref) <= REL_TOL
+    st = N.CachedStream(m)
+    outs, s0 = [], 0
+    for n in (1, 130, 4099, 777, 10**9):
+        if s0 >= T:
+            break
+        outs.append(st(x[..., s0:s0 + n].to(DEV), cond.to(DEV)))
+        s0 += n
+    assert rel_err(torch.cat(outs, -1), ref) <= REL_TOL
+    assert m.saturated() is False
+
+
+def test_batch_slicing_under_small_workspace(monkeypatch):
+    """NASR_WORKSPACE_MB bounds the activation planes: the batch is then processed in slices."""
+    monkeypatch.setenv("NASR_WORKSPACE_MB", "8")
+    cfg = O.CONFIGS["cfg2"]
+    sd = O.config_state("cfg2")
+    m = build_model(cfg, sd, DEV)
+    m.release_engine()                    # pick up the env var
+    x = O.make_input(5, 1, 20000)
+    cond = torch.rand(5, 2)
+    y = m(x.to(DEV), cond.to(DEV))        # 2 planes x 2.56 MB per clip -> slices of 1 clip
+    ref = O.forward(sd, O.config_dilations(cfg), x, cond)
+    assert rel_err(y, ref) <= REL_TOL
+    m.release_engine()
