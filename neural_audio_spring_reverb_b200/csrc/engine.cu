@@ -49,8 +49,11 @@ struct nasr_engine {
   FoldArgs* fold_dev = nullptr;
   int condCap = 0, condB = 0;
   bool fold_valid = false;
-  unsigned int* sat_flag = nullptr;   // device: a SPLIT16 write saturated during the last forward
-  unsigned int* sat_host = nullptr;   // pinned mirror
+  // "a SPLIT16 write saturated during the last forward": lives in mapped pinned host memory, so
+  // kernels raise it over PCIe only in the rare bad case and the host reads it after a stream
+  // sync without any copy. sat_flag is the device-side alias of sat_host.
+  unsigned int* sat_flag = nullptr;
+  volatile unsigned int* sat_host = nullptr;
   DevBuf plane[2];
   // streaming
   int streamB = 0;
@@ -241,8 +244,7 @@ void nasr_engine_destroy(nasr_engine* e) {
     for (auto& b : e->blocks) free_block(b);
     if (e->wout) cudaFree(e->wout);
     if (e->fold_dev) cudaFree(e->fold_dev);
-    if (e->sat_flag) cudaFree(e->sat_flag);
-    if (e->sat_host) cudaFreeHost(e->sat_host);
+    if (e->sat_host) cudaFreeHost((void*)e->sat_host);
     release(e->plane[0]); release(e->plane[1]);
     for (auto& p : e->splane) release(p);
     release(e->scratch); release(e->hx); release(e->hy); release(e->hc);
@@ -381,9 +383,8 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
   }
   if (rc == NASR_OK) {
     cudaError_t err = cudaMalloc((void**)&e->fold_dev, sizeof(FoldArgs) * n);
-    if (err == cudaSuccess) err = cudaMalloc((void**)&e->sat_flag, sizeof(unsigned int));
-    if (err == cudaSuccess) err = cudaMemset(e->sat_flag, 0, sizeof(unsigned int));
-    if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->sat_host, sizeof(unsigned int), cudaHostAllocDefault);
+    if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->sat_host, sizeof(unsigned int), cudaHostAllocMapped);
+    if (err == cudaSuccess) err = cudaHostGetDevicePointer((void**)&e->sat_flag, (void*)e->sat_host, 0);
     if (err != cudaSuccess) rc = fail(nullptr, NASR_ERR_NOMEM, "fold args / flag allocation failed");
     else *e->sat_host = 0;
   }
@@ -486,7 +487,6 @@ int nasr_saturated(nasr_engine* e, void* stream) {
   if (!e) return NASR_ERR_INVALID;
   DeviceGuard guard(e->device);
   cudaStream_t s = (cudaStream_t)stream;
-  NASR_CUDA(e, cudaMemcpyAsync(e->sat_host, e->sat_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
   NASR_CUDA(e, cudaStreamSynchronize(s));
   return *e->sat_host ? 1 : 0;
 }
@@ -530,7 +530,9 @@ static int forward_impl(nasr_engine* e, const float* x_dev, float* y_dev, int B,
       }
     }
   }
-  NASR_CUDA(e, cudaMemsetAsync(e->sat_flag, 0, sizeof(unsigned int), s));
+  // Cleared from the host: safe because work that could still raise the flag belongs to an
+  // earlier forward, whose verdict the caller either already read or chose to skip.
+  *e->sat_host = 0;
   std::vector<cudaEvent_t> ev;
   if (block_ms) {
     ev.resize(n + 1);
@@ -581,7 +583,6 @@ int nasr_forward_host(nasr_engine* e, const float* x_host, const float* cond_hos
   if (rc != NASR_OK) return rc;
   rc = nasr_forward(e, (const float*)e->hx.p, (float*)e->hy.p, B, T, stream);
   if (rc != NASR_OK) return rc;
-  NASR_CUDA(e, cudaMemcpyAsync(e->sat_host, e->sat_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
   NASR_CUDA(e, cudaMemcpyAsync(y_host, e->hy.p, yb, cudaMemcpyDeviceToHost, s));
   NASR_CUDA(e, cudaStreamSynchronize(s));
   if (*e->sat_host) {
@@ -649,7 +650,8 @@ int nasr_stream_reset(nasr_engine* e, int B, void* stream) {
   if (B < 1) return fail(e, NASR_ERR_INVALID, "B must be >= 1");
   DeviceGuard guard(e->device);
   cudaStream_t s = (cudaStream_t)stream;
-  NASR_CUDA(e, cudaMemsetAsync(e->sat_flag, 0, sizeof(unsigned int), s));
+  NASR_CUDA(e, cudaStreamSynchronize(s));
+  *e->sat_host = 0;
   const long long Tcap = (e->streamB == B && e->streamTcap > 0) ? e->streamTcap : 1024;
   if (e->streamB == B && !e->splane.empty()) {
     for (auto& q : e->splane) NASR_CUDA(e, cudaMemsetAsync(q.p, 0, q.cap, s));
