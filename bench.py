@@ -300,14 +300,17 @@ def main():
         dom_flops = sum(costs[i]["flops"] for i in mid) / len(mid) * B * T
         gbs = dom_bytes / (dom_ms * 1e-3) / 1e9
         tfs = dom_flops / (dom_ms * 1e-3) / 1e12
-        tensor_path = all(paths[i] == 1 for i in mid)
+        tensor_path = all(paths[i] in (1, 2) for i in mid)
+        ring_path = sum(1 for i in mid if paths[i] == 2) * 2 > len(mid)
         hbm_frac = gbs / pk["hbm"]
         tensor_frac = tfs / pk["bf16"]
         if tensor_path and tensor_frac >= hbm_frac:
             roof = dict(bound="tensor", achieved=tfs, peak=pk["bf16"], unit="TFLOP/s", frac=tensor_frac, traffic=None)
         else:
             roof = dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=hbm_frac, traffic=None)
-        roof.update(kernel="tc_block_kernel" if tensor_path else "generic_block_kernel (fp32 FFMA)",
+        roof.update(kernel=("ring_block_kernel" if ring_path else "tc_block_kernel") if tensor_path
+                    else "generic_block_kernel (fp32 FFMA)",
+                    issued_fp16_tflops=3.0 * tfs if tensor_path else None,   # 3 fp16 products per fp32-grade product
                     peak_source=pk["source"], launch_ms=dom_ms, hbm_gbs=gbs, hbm_frac=hbm_frac,
                     useful_tflops=tfs, bf16_peak_frac=tensor_frac, fp32_ffma_frac_of_75tf=tfs / 75.0,
                     block_ms=block_ms, block_paths=paths,

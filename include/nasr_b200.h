@@ -69,7 +69,8 @@ enum { NASR_ARCH_TCN = 0, NASR_ARCH_GCN = 1 };
 /* precision / kernel selection */
 enum {
   NASR_PATH_AUTO = 0,        /* tensor-core (tcgen05 split-16) blocks where eligible, else fp32 FFMA */
-  NASR_PATH_FP32 = 1         /* fp32 FFMA kernels only                                              */
+  NASR_PATH_FP32 = 1,        /* fp32 FFMA kernels only                                              */
+  NASR_PATH_TC_GATHER = 2    /* as AUTO, but only the tap-gather tcgen05 kernel (no accumulator ring) */
 };
 
 /*
@@ -163,7 +164,7 @@ NASR_API int64_t nasr_receptive_field(const nasr_engine* e);
 
 /* Introspection used by bench.py / tests. */
 NASR_API int64_t nasr_launch_count(const nasr_engine* e);       /* kernels launched by this handle so far   */
-NASR_API int nasr_block_path(const nasr_engine* e, int block);  /* 0 = fp32 FFMA kernel, 1 = tcgen05 kernel */
+NASR_API int nasr_block_path(const nasr_engine* e, int block);  /* 0 = fp32 FFMA, 1 = tcgen05 tap-gather, 2 = tcgen05 accumulator-ring kernel */
 NASR_API const char* nasr_version(void);
 
 #ifdef __cplusplus

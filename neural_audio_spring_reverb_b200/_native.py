@@ -12,7 +12,7 @@ from pathlib import Path
 NASR_MAX_BLOCKS = 64
 NASR_OK, NASR_ERR_INVALID, NASR_ERR_CUDA, NASR_ERR_STATE, NASR_ERR_NOMEM = 0, -1, -2, -3, -4
 ARCH_TCN, ARCH_GCN = 0, 1
-PATH_AUTO, PATH_FP32 = 0, 1
+PATH_AUTO, PATH_FP32, PATH_TC_GATHER = 0, 1, 2
 
 # NASR_LIB selects a tuning variant built with `python -m ...build --out=...` (dev use only)
 LIB_PATH = Path(os.environ.get("NASR_LIB") or Path(__file__).resolve().parent / "libnasr_b200.so")

@@ -4,6 +4,7 @@
 #include "../../include/nasr_b200.h"
 #include "common.cuh"
 #include "tc_block.cuh"
+#include "ring_block.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -33,7 +34,7 @@ struct BlockState {
   int* perm = nullptr;                        // conv channel -> index in scale/shift ([tanh | sigmoid] halves padded)
   float *scale = nullptr, *shift = nullptr;  // [condCap][Wp]
   float* w0 = nullptr;                       // first block: conv weights [k][Cin][W], original order
-  uint16_t* wtc = nullptr;                   // tcgen05 path: split-fp16 weight tiles (tc_pack_weights)
+  uint16_t* wtc = nullptr;                   // tcgen05 paths: split-fp16 weight tiles (tc_pack_weights / ring_pack_weights)
   float inv_sw = 1.f, inv_sr = 1.f;
 };
 
@@ -45,6 +46,7 @@ struct nasr_engine {
   int C = 0, Cp = 0;
   std::vector<BlockState> blocks;
   std::vector<TcMapCache> tc_cache;   // per block: last TMA descriptors
+  std::vector<RingMapCache> ring_cache;
   float* wout = nullptr;  // [out_ch][Cp]
   FoldArgs* fold_dev = nullptr;
   int condCap = 0, condB = 0;
@@ -66,6 +68,7 @@ struct nasr_engine {
   mutable std::string err;
   int64_t launches = 0;
   int64_t sat_fallbacks = 0;
+  bool pdl = true;   // NASR_PDL=0 turns programmatic dependent launch off (dev)
 };
 
 namespace {
@@ -206,6 +209,17 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
     t.scale = a.scale; t.shift = a.shift; t.slope = a.slope; t.inv_sw = bs.inv_sw; t.inv_sr = bs.inv_sr;
     t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_flag;
     err = launch_tc_block(L, s);
+  } else if (allow_tc && tc_chain && bs.path == 2) {
+    RingLaunch L{};
+    L.cache = &e->ring_cache[i];
+    L.in = a.in; L.in_rows = a.in_rows; L.in_clip_stride_elems = a.in_clip_stride;
+    L.wpacked = bs.wtc; L.arch = e->desc.arch; L.sm_count = e->sm_count; L.pdl = e->pdl;
+    RingArgs& t = L.a;
+    t.out = a.out; t.out_fmt = a.out_fmt; t.out_clip_stride = a.out_clip_stride; t.out_rows = a.out_rows;
+    t.out_row0 = a.out_row0; t.in_row0 = a.in_row0; t.B = a.B; t.T = a.T; t.k = a.k; t.d = a.d;
+    t.scale = a.scale; t.shift = a.shift; t.ld_affine = bs.Wp; t.slope = a.slope; t.inv_sw = bs.inv_sw; t.inv_sr = bs.inv_sr;
+    t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_flag;
+    err = launch_ring_block(L, s);
   } else {
     err = cudaErrorNotSupported;
     if (bs.w0 && allow_tc) err = launch_first_block(a, bs.w0, e->sm_count, s);
@@ -220,6 +234,9 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
 
 // bytes of one activation plane row (CL fp32 and SPLIT16 are the same size)
 inline size_t plane_row_bytes(const nasr_engine* e) { return (size_t)e->Cp * 4; }
+// tail slack of every activation plane: the ring kernel's grouped TMA view may read (never use) rows past
+// the last clip (ring_block.cuh)
+inline size_t plane_slack_bytes() { return (size_t)RB_SLACK_ROWS * 128; }
 
 }  // namespace
 
@@ -291,6 +308,8 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
   const bool gcn = desc->arch == NASR_ARCH_GCN;
   e->blocks.resize(n);
   e->tc_cache.resize(n);
+  e->ring_cache.resize(n);
+  if (const char* env = getenv("NASR_PDL")) e->pdl = atoi(env) != 0;
   const float* p = w;
   std::vector<FoldArgs> fold(n);
   int rc = NASR_OK;
@@ -309,11 +328,18 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
     b.k = k; b.d = desc->dilations[i];
     b.hist = (long long)(k - 1) * b.d;
     b.NC = pick_nc(desc->arch, Cp);
-    const bool want_tc = desc->path == NASR_PATH_AUTO;
-    auto is_tc = [&](int blk) { return want_tc && blk >= 1 && blk < n && tc_eligible(desc->arch, C, C, k); };
-    b.path = is_tc(i) ? 1 : 0;
-    b.in_fmt = (i == 0) ? FMT_NCT : (b.path == 1 ? FMT_SPLIT16 : FMT_CL);
-    b.out_fmt = (i == n - 1) ? FMT_FINAL : (is_tc(i + 1) ? FMT_SPLIT16 : FMT_CL);
+    // kernel of block blk: 0 = fp32 FFMA, 1 = tcgen05 tap-gather (tc_block.cu), 2 = tcgen05 accumulator ring
+    // (ring_block.cu; the GCN ring kernel splits the channels over two CTAs and cannot fuse out_net)
+    auto path_of = [&](int blk) {
+      if (desc->path == NASR_PATH_FP32 || blk < 1 || blk >= n) return 0;
+      if (desc->path == NASR_PATH_AUTO && ring_eligible(desc->arch, C, C, k, desc->dilations[blk]) &&
+          !(gcn && blk == n - 1))
+        return 2;
+      return tc_eligible(desc->arch, C, C, k) ? 1 : 0;
+    };
+    b.path = path_of(i);
+    b.in_fmt = (i == 0) ? FMT_NCT : (b.path != 0 ? FMT_SPLIT16 : FMT_CL);
+    b.out_fmt = (i == n - 1) ? FMT_FINAL : (path_of(i + 1) != 0 ? FMT_SPLIT16 : FMT_CL);
     if (b.Wp / b.NC > 16) { rc = fail(nullptr, NASR_ERR_INVALID, "channel count too large for the generic kernel"); break; }
 
     // packed column of each conv channel in the generic kernel's weight tiles (GCN: the tanh and
@@ -367,6 +393,13 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
     if (b.path == 1) {
       std::vector<uint16_t> h_wtc;
       tc_pack_weights(desc->arch, k, conv_w, res_w, h_wtc, &b.inv_sw, &b.inv_sr);
+      up(&b.wtc, h_wtc);
+    } else if (b.path == 2) {
+      std::vector<uint16_t> h_wtc, part;
+      for (int g = 0; g < ring_groups(desc->arch); ++g) {
+        ring_pack_weights(desc->arch, g, k, conv_w, res_w, part, &b.inv_sw, &b.inv_sr);
+        h_wtc.insert(h_wtc.end(), part.begin(), part.end());
+      }
       up(&b.wtc, h_wtc);
     }
     if (desc->has_film) {
@@ -524,9 +557,9 @@ static int forward_impl(nasr_engine* e, const float* x_dev, float* y_dev, int B,
       slice = (int)fit;
     }
     for (int q = 0; q < nplanes; ++q) {
-      if (e->plane[q].cap < per_clip * slice) {
+      if (e->plane[q].cap < per_clip * slice + plane_slack_bytes()) {
         NASR_CUDA(e, cudaStreamSynchronize(s));
-        NASR_CUDA(e, ensure(e->plane[q], per_clip * slice));
+        NASR_CUDA(e, ensure(e->plane[q], per_clip * slice + plane_slack_bytes()));
       }
     }
   }
@@ -604,7 +637,7 @@ int nasr_forward_host(nasr_engine* e, const float* x_host, const float* cond_hos
 static size_t splane_bytes(const nasr_engine* e, int i, int B, long long Tcap) {
   const BlockState& b = e->blocks[i];
   if (i == 0) return (size_t)B * e->desc.in_ch * (b.hist + Tcap) * sizeof(float);
-  return (size_t)B * (b.hist + Tcap) * plane_row_bytes(e);
+  return (size_t)B * (b.hist + Tcap) * plane_row_bytes(e) + plane_slack_bytes();
 }
 
 static int stream_alloc(nasr_engine* e, int B, long long Tcap, cudaStream_t s, bool keep_history) {

@@ -1,0 +1,716 @@
+// Input-stationary tcgen05 block kernel for 32 -> 32 channel TCN / GCN blocks (sm_100a).
+//
+// Same arithmetic as generic_block.cu / tc_block.cu (reference src/nasr/networks/tcn.py:73-86,
+// gcn.py:53-61, custom_layers.py:32-42,85-88) and the same SPLIT16 planes and 3-term fp16
+// product as tc_block.cu, but the implicit GEMM is turned around so that the small N of the
+// per-tap product (32 conv channels) stops costing a full A-operand fetch per tap:
+//
+//   y[t] = sum_s V_s x[t - s*d]         (s = taps counted backwards, V_s = W[:, :, k-1-s])
+//
+// A CTA walks time in steps of d: tile X_i holds 128 rows whose successors X_{i+1} are the same
+// rows d samples later.  X_i contributes V_s X_i to the outputs of step i + s, for every s at
+// once, so ONE instruction per 16-channel slice multiplies the tile with the stacked weights
+// [V_0; V_1; ...; V_{k-1}; R] (N up to 256 per instruction) and scatters into a ring of k + 1
+// accumulator slots of 32 TMEM columns: slot (i + s) mod (k+1) collects y_{i+s}; the extra slot
+// takes the 1x1 residual R x_i.  After step i the slot of y_i is complete and is drained by
+// the epilogue while step i + 1 runs; the slot it frees is the one step i + 1 starts afresh.
+// Each input tile is fetched from shared memory 6 times per step (2 channel slices x 3 product
+// terms) instead of 6 times per tap, which lifts the kernel from the operand-fetch limit of
+// small-N MMAs (tc_block.cu) to the tensor-pipe math limit.
+//
+// Tiles whose rows are d apart: for d >= 128 a tile is 128 consecutive rows of one period
+// (mode L, lanes beyond d masked); for d < 128 a tile is G = 128/d groups of d consecutive rows,
+// the groups n*d rows apart (n = steps per span), so the n steps of a span cover G*n*d
+// contiguous rows (mode S, one 4-D TMA box per step).  A span starts with k - 1 warm-up steps
+// that only feed later outputs.
+//
+// GCN (conv width 64) does not fit 15 x 64 columns: the gate channels are split into two
+// groups of 16 (tanh and sigmoid halves side by side in one 32-column slot), one group per CTA.
+#include "common.cuh"
+#include "sm100.cuh"
+#include "ring_block.cuh"
+#include <cuda_fp16.h>
+#include <cmath>
+#include <cstdlib>
+
+#ifndef RB_ESETS
+#define RB_ESETS 2        // epilogue warp sets (4 warps each); set e drains steps with index % ESETS == e
+#endif
+
+namespace nasr {
+using namespace sm100;
+
+namespace {
+
+__device__ __forceinline__ bool rb_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// 32 lanes x 32 columns <- 0 (the epilogue hands its slots back cleared, so every steady-state MMA accumulates)
+__device__ __forceinline__ void tmem_zero_32x32(uint32_t taddr) {
+  const uint32_t z = 0;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      :
+      : "r"(taddr), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float rb_tanh(float x) {
+  const float e = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+__device__ __forceinline__ float rb_sigmoid(float x) {
+  const float e = __expf(-x);
+  return e > 1e30f ? 0.0f : __fdividef(1.0f, 1.0f + e);
+}
+
+// one span = n consecutive steps of one strip (clip b, lane l)
+struct Span {
+  int b, l, nsteps;
+  long long m;
+  __device__ bool set(const RingArgs& a, long long sp) {
+    if (sp >= a.total_spans) return false;
+    const long long strip = sp / a.spans_per_strip;
+    m = sp - strip * a.spans_per_strip;
+    b = (int)(strip / a.L);
+    l = (int)(strip - (long long)b * a.L);
+    long long left;
+    if (a.mode == 0) {
+      const long long row0 = m * a.G * a.S;                // first row of the span
+      left = (a.T - row0 + a.d - 1) / a.d;                 // steps until group 0 leaves the clip
+    } else {
+      left = a.NP - m * a.n;
+    }
+    nsteps = (int)(left < a.n ? left : a.n);
+    return nsteps > 0;
+  }
+};
+
+}  // namespace
+
+template <int ARCH>
+__global__ void __launch_bounds__((4 * RB_ESETS + 2) * 32, 1)
+ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map, const RingArgs a) {
+  constexpr int ESETS = RB_ESETS;
+  constexpr int EPI_WARPS = 4 * ESETS, PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
+  constexpr int NO = (ARCH == 1) ? 16 : 32;   // output channels per thread row
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = smem;                                            // stages x 16 KB input tiles
+  uint8_t* wsm = ring + (size_t)a.stages * RB_TILE_BYTES;           // NW x 4 KB stacked weights (wrapping copy: a chunk never wraps)
+  uint8_t* estage = wsm + (size_t)a.NW * 4096;                      // per epilogue warp: 4 KB row staging
+  uint8_t* eaff = estage + (size_t)EPI_WARPS * 4096;                // per epilogue warp: 64 floats scale/shift
+  uint64_t* bars = (uint64_t*)(eaff + (size_t)EPI_WARPS * 256);
+  uint64_t* full = bars;                       // [RB_MAX_STAGES]
+  uint64_t* empty = full + RB_MAX_STAGES;      // [RB_MAX_STAGES]
+  uint64_t* done = empty + RB_MAX_STAGES;      // [2]  step complete -> epilogue
+  uint64_t* drained = done + 2;                // [1]  epilogue has read its slots -> MMA
+  uint64_t* wfull = drained + 1;               // [1]
+  uint32_t* tmem_slot = (uint32_t*)(wfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int km1 = a.k - 1, NS = a.NS;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RB_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&done[0], 1);
+    mbar_init(&done[1], 1);
+    mbar_init(drained, 4);
+    mbar_init(wfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == PRODUCER_WARP) {
+    tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // let the next kernel of the stream get scheduled as CTAs of this one retire (its own
+  // griddepcontrol.wait keeps it from touching our output before we are completely done)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  // GCN: CTA parity picks the channel group; spans are dealt round-robin to the CTAs of a group
+  const int n_grp = a.n_grp;
+  const int grp = (int)(blockIdx.x % n_grp);
+  const long long sp0 = blockIdx.x / n_grp, sp_stride = gridDim.x / n_grp;
+
+  if (warp == PRODUCER_WARP) {
+    // ================================ TMA producer ================================
+    if (rb_elect_one()) {
+      prefetch_tensormap(&in_map);
+      mbar_arrive_expect_tx(wfull, (uint32_t)(a.NW * 4096));
+      for (int p = 0; p < a.NW; ++p)
+        tma_load_3d(wsm + (size_t)p * 4096, &w_map, wfull, 0, (grp * NS + (p >= NS ? p - NS : p)) * 32, 0);
+      // everything above is independent of the previous kernel in the stream
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      const uint32_t tile_bytes = a.mode == 0 ? (uint32_t)(a.G * a.d * 128) : (uint32_t)RB_TILE_BYTES;
+      int st = 0;
+      uint32_t empty_phase = ~0u;
+      Span s;
+      for (long long sp = sp0; s.set(a, sp); sp += sp_stride) {
+        for (int i = -km1; i < s.nsteps; ++i) {
+          mbar_wait(&empty[st], (empty_phase >> st) & 1u);
+          empty_phase ^= 1u << st;
+          mbar_arrive_expect_tx(&full[st], tile_bytes);
+          if (a.mode == 0) {
+            long long r0 = a.in_row0 + (long long)i * a.d;
+            long long j0 = s.m * a.G;
+            if (r0 < 0) {   // same rows through earlier group indices; j < 0 is the causal zero pad
+              const long long q = (-r0 + a.S - 1) / a.S;
+              r0 += q * a.S;
+              j0 -= q;
+            }
+            tma_load_4d(ring + (size_t)st * RB_TILE_BYTES, &in_map, &full[st], 0, (int)r0, (int)j0, s.b);
+          } else {
+            const long long row = a.in_row0 + (s.m * a.n + i) * a.d + 128LL * s.l;
+            tma_load_3d(ring + (size_t)st * RB_TILE_BYTES, &in_map, &full[st], 0, (int)row, s.b);
+          }
+          st = (st + 1 == a.stages) ? 0 : st + 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == MMA_WARP) {
+    // ================================ MMA issuer (one thread) ================================
+    if (rb_elect_one()) {
+      constexpr uint32_t idesc0 = make_idesc(FMT_F16, FMT_F16, 128, 0);
+      const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t w_lo32 = ((smem_u32(wsm) & 0x3FFFFu) >> 4) | (1u << 16);
+      // product term c: A chunk offset / B chunk offset in 16-byte units within the 128-byte row
+      // (row = [hi ch 0-15 | hi ch 16-31 | lo ch 0-15 | lo ch 16-31])
+      //   xh*wh (2 slices), xh*wl (2 slices), xl*wh (2 slices)
+      constexpr uint32_t a_off[6] = {0, 2, 0, 2, 4, 6};
+      constexpr uint32_t b_off[6] = {0, 2, 4, 6, 0, 2};
+      // D[:, 32*slot .. 32*(slot+nb)) (+)= X * [blocks b0 .. b0+nb)^T for product term c
+      auto mma = [&](uint32_t a_lo, int slot, int b0, int nb, int c, uint32_t acc) {
+        const uint32_t idesc = idesc0 | ((uint32_t)(nb * 4) << 17);     // N = 32 * nb
+        const uint64_t da = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (a_lo + a_off[c]);
+        const uint64_t db = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (w_lo32 + (uint32_t)b0 * 256u + b_off[c]);
+        if (!(a.dbg & 2)) umma_f16(tmem + (uint32_t)(slot * 32), da, db, idesc, acc);
+      };
+      // steady-state chunks of the slot ring: [0, h0) and [h0, NS)
+      const int nchunk = NS > 8 ? 2 : 1;
+      const int h0 = nchunk == 2 ? (NS + 1) / 2 : NS;
+      mbar_wait(wfull, 0);
+      tc_fence_after();
+      int st = 0;
+      uint32_t full_phase = 0, drain_phase = 0, e = 0;
+      bool pending = false;
+      auto wait_drain = [&]() {
+        if (pending) {
+          mbar_wait(drained, drain_phase);
+          drain_phase ^= 1u;
+          pending = false;
+          tc_fence_after();
+        }
+      };
+      Span s;
+      for (long long sp = sp0; s.set(a, sp); sp += sp_stride) {
+        // ---- warm-up steps i = -(k-1) .. 0: exact block ranges, slots 0 .. i+k-1 (no wrap); the last
+        //      block of the range (and the residual at i = 0) starts its slot (accumulate = 0) ----
+        wait_drain();   // the previous span's last outputs have left TMEM
+        for (int i = -km1; i <= 0; ++i) {
+          mbar_wait(&full[st], (full_phase >> st) & 1u);
+          full_phase ^= 1u << st;
+          tc_fence_after();
+          const uint32_t a_lo = ring_lo + (uint32_t)st * (RB_TILE_BYTES >> 4);
+          const int len = i + a.k;                  // blocks -i .. k-1  ->  slots 0 .. len-1
+          const int nf = len - 1;                   // slots already started
+          const int nfr = (i == 0) ? 2 : 1;         // slots started now: y_{len-1} (+ residual of step 0)
+          const int tb = nf + nfr;
+          if (nf > 8) { mma(a_lo, 0, -i, 8, 0, 1u); mma(a_lo, 8, -i + 8, nf - 8, 0, 1u); }
+          else if (nf > 0) mma(a_lo, 0, -i, nf, 0, 1u);
+          mma(a_lo, nf, km1, nfr, 0, 0u);
+#pragma unroll
+          for (int c = 1; c < 6; ++c) {
+            if (tb > 8) { mma(a_lo, 0, -i, 8, c, 1u); mma(a_lo, 8, -i + 8, tb - 8, c, 1u); }
+            else mma(a_lo, 0, -i, tb, c, 1u);
+          }
+          umma_commit(&empty[st]);
+          if (i == 0) {
+            umma_commit(&done[e & 1u]);
+            pending = true;
+            ++e;
+          }
+          st = (st + 1 == a.stages) ? 0 : st + 1;
+        }
+        // ---- steady state: every block, fixed chunks of the ring; slot (i + b) mod NS <- block b.  The two
+        //      slots that start at step i, (i-2) and (i-1) mod NS, were read AND zeroed by epilogue(i-1), so
+        //      every instruction accumulates; the chunk that holds them waits for that drain. ----
+        int islot = 1 % NS;
+        for (int i = 1; i < s.nsteps; ++i) {
+          mbar_wait(&full[st], (full_phase >> st) & 1u);
+          full_phase ^= 1u << st;
+          tc_fence_after();
+          const uint32_t a_lo = ring_lo + (uint32_t)st * (RB_TILE_BYTES >> 4);
+          const int f1 = islot >= 1 ? islot - 1 : islot - 1 + NS;     // (i-1) mod NS
+          const int f2 = f1 >= 1 ? f1 - 1 : f1 - 1 + NS;              // (i-2) mod NS
+          // block of slot 0 is (0 - i) mod NS; the weights are stored twice so that a chunk never wraps
+          const int bz = islot == 0 ? 0 : NS - islot;
+          if (nchunk == 2) {
+            const bool fresh0 = f1 < h0 || f2 < h0, fresh1 = f1 >= h0 || f2 >= h0;
+            const int b1 = bz + h0 >= NS ? bz + h0 - NS : bz + h0;
+            if (!fresh0) {
+#pragma unroll
+              for (int c = 0; c < 6; ++c) mma(a_lo, 0, bz, h0, c, 1u);
+              wait_drain();
+#pragma unroll
+              for (int c = 0; c < 6; ++c) mma(a_lo, h0, b1, NS - h0, c, 1u);
+            } else if (!fresh1) {
+#pragma unroll
+              for (int c = 0; c < 6; ++c) mma(a_lo, h0, b1, NS - h0, c, 1u);
+              wait_drain();
+#pragma unroll
+              for (int c = 0; c < 6; ++c) mma(a_lo, 0, bz, h0, c, 1u);
+            } else {
+              wait_drain();
+#pragma unroll
+              for (int c = 0; c < 6; ++c) { mma(a_lo, 0, bz, h0, c, 1u); mma(a_lo, h0, b1, NS - h0, c, 1u); }
+            }
+          } else {
+            wait_drain();
+#pragma unroll
+            for (int c = 0; c < 6; ++c) mma(a_lo, 0, bz, NS, c, 1u);
+          }
+          umma_commit(&empty[st]);          // the tile may be overwritten once these MMAs have read it
+          umma_commit(&done[e & 1u]);       // y_i and its residual are complete
+          pending = true;
+          ++e;
+          st = (st + 1 == a.stages) ? 0 : st + 1;
+          islot = islot + 1 == NS ? 0 : islot + 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue ================================
+    // Thread = one tile row (TMEM lane).  Rows are staged through a warp-private, XOR-swizzled
+    // shared-memory tile so that the global stores are whole 128-byte rows per 8 lanes
+    // (a thread storing its own row 16 bytes at a time costs 32 LSU wavefronts per instruction).
+    constexpr int NCH = NO / 4;              // 16-byte chunks per staged row: 8 (TCN) / 4 (GCN group)
+    constexpr int RPI = 32 / NCH;            // rows per coalesced store instruction: 4 / 8
+    const int eset = warp >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;                       // tile row owned by this thread
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+    uint8_t* stage = estage + (size_t)warp * 4096;
+    float* aff = reinterpret_cast<float*>(eaff + (size_t)warp * 256);     // [0,32) scale * inv_sw, [32,64) shift
+    // where this row sits in time relative to the step's first row
+    long long off;
+    bool lane_ok;
+    if (a.mode == 0) {
+      const int jg = row / a.d, rr = row - jg * a.d;
+      off = (long long)jg * a.S + rr;
+      lane_ok = jg < a.G;
+    } else {
+      off = row;
+      lane_ok = true;
+    }
+    // the rows this lane stores after the transpose: row_q = quad*32 + RPI*q + lane/NCH, chunk = lane % NCH
+    const int my_c = lane % NCH, my_r = lane / NCH;
+    int offq[NCH];
+    uint32_t okq = 0;
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) {
+      const int rq = quad * 32 + RPI * q + my_r;
+      if (a.mode == 0) {
+        const int jg = rq / a.d, rr = rq - jg * a.d;
+        offq[q] = (int)((long long)jg * a.S) + rr;
+        if (jg < a.G) okq |= 1u << q;
+      } else {
+        offq[q] = rq;
+        okq |= 1u << q;
+      }
+    }
+    // byte offset of chunk my_c inside the 128-byte output row
+    int cbyte;
+    if (ARCH == 0) cbyte = my_c * 16;
+    else if (a.out_fmt == FMT_SPLIT16) cbyte = (my_c < 2 ? 0 : 64) + grp * 32 + (my_c & 1) * 16;
+    else cbyte = grp * 64 + my_c * 16;
+    const float slope = a.slope, inv_sr = a.inv_sr;
+    uint32_t e = 0;
+    Span s;
+    for (long long sp = sp0; s.set(a, sp); sp += sp_stride) {
+      const float* sc = a.scale + (long long)s.b * a.ld_affine;
+      const float* sh = a.shift + (long long)s.b * a.ld_affine;
+      __syncwarp();
+      if (ARCH == 0) {
+        aff[lane] = __ldg(sc + lane) * a.inv_sw;
+        aff[32 + lane] = __ldg(sh + lane);
+      } else {   // lanes 0..15: tanh half of this group, 16..31: sigmoid half (one padded width = 32 further)
+        const int src = (lane < 16) ? grp * 16 + lane : 32 + grp * 16 + (lane - 16);
+        aff[lane] = __ldg(sc + src) * a.inv_sw;
+        aff[32 + lane] = __ldg(sh + src);
+      }
+      __syncwarp();
+      long long t_span;        // time of tile row 0 at step 0
+      uint32_t okm = okq;
+      bool ok = lane_ok;
+      if (a.mode == 0) {
+        t_span = s.m * a.G * a.S;
+      } else {
+        t_span = s.m * a.n * (long long)a.d + 128LL * s.l;
+        ok = (128LL * s.l + row) < a.d;
+        okm = 0;
+#pragma unroll
+        for (int q = 0; q < NCH; ++q)
+          if (128LL * s.l + offq[q] < a.d) okm |= 1u << q;
+      }
+      uint8_t* out_clip = reinterpret_cast<uint8_t*>(a.out) + (long long)s.b * a.out_clip_stride * (a.out_fmt == FMT_SPLIT16 ? 2 : 4);
+      for (int i = 0; i < s.nsteps; ++i, ++e) {
+        if ((int)(e % ESETS) != eset) continue;
+        const long long t0 = t_span + (long long)i * a.d;
+        const int cslot = i % NS, rslot = (i + NS - 1) % NS;
+        mbar_wait(&done[e & 1u], (e >> 1) & 1u);
+        tc_fence_after();
+        float o[NO];
+        if (a.dbg & 1) {   // dev: drain only
+          uint32_t u[32];
+          tmem_ld_32x32(lane_base + (uint32_t)(cslot * 32), u);
+          tmem_ld_wait();
+          if (!(a.dbg & 4)) {
+            tmem_zero_32x32(lane_base + (uint32_t)(cslot * 32));
+            tmem_zero_32x32(lane_base + (uint32_t)(rslot * 32));
+            tmem_st_wait();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(drained);
+          if (u[0] == 0x12345678u && ok) *a.sat_flag = 2u;
+          continue;
+        }
+        if (ARCH == 0) {
+          uint32_t u[32], v[32];
+          tmem_ld_32x32(lane_base + (uint32_t)(cslot * 32), u);
+          tmem_ld_32x32(lane_base + (uint32_t)(rslot * 32), v);
+          tmem_ld_wait();
+          tmem_zero_32x32(lane_base + (uint32_t)(cslot * 32));
+          tmem_zero_32x32(lane_base + (uint32_t)(rslot * 32));
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(drained);
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(aff + c);
+            const float4 h4 = *reinterpret_cast<const float4*>(aff + 32 + c);
+            const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, hh[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float y = fmaf(__uint_as_float(u[c + q]), ss[q], hh[q]);
+              const float p = fmaxf(y, 0.f) + slope * fminf(y, 0.f);
+              o[c + q] = fmaf(__uint_as_float(v[c + q]), inv_sr, p);
+            }
+          }
+        } else {
+          uint32_t u[32], v[16];
+          tmem_ld_32x32(lane_base + (uint32_t)(cslot * 32), u);
+          tmem_ld_32x16(lane_base + (uint32_t)(rslot * 32), v);
+          tmem_ld_wait();
+          tmem_zero_32x32(lane_base + (uint32_t)(cslot * 32));
+          tmem_zero_32x32(lane_base + (uint32_t)(rslot * 32));
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(drained);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float yt = fmaf(__uint_as_float(u[c]), aff[c], aff[32 + c]);
+            const float ys = fmaf(__uint_as_float(u[16 + c]), aff[16 + c], aff[48 + c]);
+            o[c] = fmaf(__uint_as_float(v[c]), inv_sr, rb_tanh(yt) * rb_sigmoid(ys));
+          }
+        }
+
+        if (a.out_fmt == FMT_FINAL) {
+          if (ARCH == 0) {   // out_net 1x1 (+ tanh), row-local (single group only); lanes = consecutive samples
+            const long long t = t0 + off;
+            const bool valid = ok && t < a.T;
+            for (int oc = 0; oc < a.out_ch; ++oc) {
+              float y = 0.f;
+#pragma unroll
+              for (int c = 0; c < NO; ++c) y = fmaf(o[c], __ldg(a.wout + oc * 32 + c), y);
+              if (a.final_tanh) y = tanhf(y);
+              if (valid)
+                ((float*)a.out)[(long long)s.b * a.out_clip_stride + (long long)oc * a.out_rows + a.out_row0 + t] = y;
+            }
+          }
+          continue;
+        }
+
+        // ---- stage the row (16-byte chunks, XOR-swizzled) ----
+        uint4 ch[NCH];
+        if (a.out_fmt == FMT_SPLIT16) {
+          uint32_t hi[NO / 2], lo[NO / 2];
+          float vmax = 0.f;
+#pragma unroll
+          for (int c = 0; c < NO; ++c) vmax = fmaxf(vmax, fabsf(o[c]));
+          if (vmax > 65504.f && ok && t0 + off < a.T) *a.sat_flag = 1u;
+#pragma unroll
+          for (int c = 0; c < NO; c += 2) {
+            const float x0 = fminf(fmaxf(o[c], -65504.f), 65504.f), x1 = fminf(fmaxf(o[c + 1], -65504.f), 65504.f);
+            const __half2 h = __floats2half2_rn(x0, x1);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+            hi[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[c >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+#pragma unroll
+          for (int q = 0; q < NCH / 2; ++q) {
+            ch[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+            ch[NCH / 2 + q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+          }
+        } else {   // FMT_CL: fp32 row
+#pragma unroll
+          for (int q = 0; q < NCH; ++q)
+            ch[q] = make_uint4(__float_as_uint(o[4 * q]), __float_as_uint(o[4 * q + 1]), __float_as_uint(o[4 * q + 2]),
+                               __float_as_uint(o[4 * q + 3]));
+        }
+        const int wsw = (NCH == 8) ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+        for (int q = 0; q < NCH; ++q)
+          *reinterpret_cast<uint4*>(stage + lane * (NCH * 16) + ((q ^ wsw) * 16)) = ch[q];
+        __syncwarp();
+        // ---- coalesced stores: 8 (4) lanes per row ----
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+          const int rl = RPI * q + my_r;       // row within the warp's 32
+          const int rsw = (NCH == 8) ? (rl & 7) : ((rl >> 1) & 3);
+          const uint4 val = *reinterpret_cast<const uint4*>(stage + rl * (NCH * 16) + ((my_c ^ rsw) * 16));
+          const long long t = t0 + offq[q];
+          if (((okm >> q) & 1u) && t < a.T)
+            *reinterpret_cast<uint4*>(out_clip + (a.out_row0 + t) * 128LL + cbyte) = val;
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == PRODUCER_WARP) tmem_dealloc(tmem, (uint32_t)a.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------ host side
+
+// weight blocks held in shared memory: block p = block p mod NS, far enough that a steady-state chunk
+// (<= ceil(NS/2) slots, or all NS when NS <= 8) starting at any block never wraps
+static int rb_weight_blocks(int NS) { return NS + (NS > 8 ? (NS + 1) / 2 : NS) - 1; }
+static size_t rb_smem_bytes(int NS, int stages) {
+  return (size_t)stages * RB_TILE_BYTES + (size_t)rb_weight_blocks(NS) * 4096 + (size_t)(4 * RB_ESETS) * (4096 + 256) + 512 +
+         1024;
+}
+
+int ring_groups(int arch) { return arch == 1 ? 2 : 1; }
+
+bool ring_eligible(int arch, int Cin, int C, int k, int d) {
+  if (Cin != 32 || C != 32 || k < 1 || k + 1 > RB_MAX_SLOTS || d < 1) return false;
+  (void)arch;
+  // share of the 128 tile rows that carry real samples
+  double eff;
+  if (d < 128) eff = (double)((128 / d) * d) / 128.0;
+  else eff = (double)d / (128.0 * ((d + 127) / 128));
+  return eff >= 0.75;
+}
+
+// Stacked weights of one channel group: NS = k + 1 blocks of 32 rows x 128 B,
+//   block s < k : V_s = conv weight tap k-1-s;  row n = conv channel (TCN: n; GCN group g: rows 0..15 = tanh
+//                 channels 16g.., rows 16..31 = sigmoid channels 32 + 16g..)
+//   block k     : residual 1x1 (GCN: rows 0..15 = output channels 16g.., rows 16..31 zero)
+// each row = 32 x fp16 hi(w * S) then 32 x fp16 lo(w * S); S = power of two with max|w| * S in [512, 1024).
+void ring_pack_weights(int arch, int grp, int k, const float* conv_w /*[W][32][k]*/, const float* res_w /*[32][32]*/,
+                       std::vector<uint16_t>& out, float* inv_sw, float* inv_sr) {
+  const int W = arch == 1 ? 64 : 32, C = 32, NS = k + 1;
+  out.assign((size_t)NS * 32 * 64, 0);
+  auto pow2_scale = [](const float* w, size_t n) {
+    float mx = 0.f;
+    for (size_t i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(w[i]));
+    if (!(mx > 0.f) || !isfinite(mx)) return 1.0f;
+    int e;
+    frexpf(mx, &e);
+    return ldexpf(1.0f, 10 - e);
+  };
+  const float sw = pow2_scale(conv_w, (size_t)W * C * k), sr = pow2_scale(res_w, (size_t)C * C);
+  *inv_sw = 1.0f / sw;
+  *inv_sr = 1.0f / sr;
+  auto put = [&](int block, int row, int ci, float v) {
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    const size_t base = ((size_t)block * 32 + row) * 64;
+    out[base + ci] = __half_as_ushort(h);
+    out[base + 32 + ci] = __half_as_ushort(l);
+  };
+  for (int s = 0; s < k; ++s) {
+    const int j = k - 1 - s;
+    for (int n = 0; n < 32; ++n) {
+      int ch;
+      if (arch == 0) ch = n;
+      else ch = (n < 16) ? 16 * grp + n : 32 + 16 * grp + (n - 16);
+      for (int ci = 0; ci < C; ++ci) put(s, n, ci, conv_w[((size_t)ch * C + ci) * k + j] * sw);
+    }
+  }
+  const int n_res = arch == 0 ? 32 : 16;
+  for (int n = 0; n < n_res; ++n) {
+    const int ch = arch == 0 ? n : 16 * grp + n;
+    for (int ci = 0; ci < C; ++ci) put(k, n, ci, res_w[(size_t)ch * C + ci] * sr);
+  }
+}
+
+static bool make_group_map(CUtensorMap* map, const void* base, uint64_t rext, uint64_t jext, uint64_t clips,
+                           uint64_t S_rows, uint64_t clip_stride_elems, uint32_t d, uint32_t G) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {64, rext, jext, clips};
+  cuuint64_t strides[3] = {128, S_rows * 128, clip_stride_elems * 2};
+  cuuint32_t box[4] = {64, d, G, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
+  RingArgs a = L.a;
+  if (a.B <= 0 || a.T <= 0) return cudaSuccess;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("NASR_RB_DBG"); dbg = e ? atoi(e) : 0; }
+    a.dbg = dbg;
+  }
+  const int n_grp = ring_groups(L.arch);
+  a.n_grp = n_grp;
+  a.NS = a.k + 1;
+  if (a.NS > RB_MAX_SLOTS) return cudaErrorInvalidConfiguration;
+  a.NW = rb_weight_blocks(a.NS);
+  a.tmem_cols = 32;
+  while (a.tmem_cols < a.NS * 32) a.tmem_cols *= 2;
+  int stages = RB_MAX_STAGES;
+  while (stages > 2 && rb_smem_bytes(a.NS, stages) > 227 * 1024) --stages;
+  a.stages = stages;
+  const size_t smem = rb_smem_bytes(a.NS, stages);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+
+  // ---- span length: n steps per span; every span pays k - 1 warm-up steps (loads + partial MMAs) ----
+  long long steps_per_strip;   // steps a whole strip needs when it is one span
+  long long strips;
+  if (a.d < 128) {
+    a.mode = 0; a.G = 128 / a.d; a.L = 1;
+    steps_per_strip = (a.T + (long long)a.G * a.d - 1) / ((long long)a.G * a.d);
+    strips = a.B;
+  } else {
+    a.mode = 1; a.G = 1; a.L = (a.d + 127) / 128;
+    a.NP = (a.T + a.d - 1) / a.d;
+    steps_per_strip = a.NP;
+    strips = (long long)a.B * a.L;
+  }
+  const long long ctas = L.sm_count / n_grp > 0 ? L.sm_count / n_grp : 1;   // span walkers per group
+  long long n_max = 512;
+  if (a.mode == 0) {
+    const long long cap = (RB_SLACK_ROWS - (long long)(a.k + 1) * a.d - a.in_row0) / a.d;   // over-read bound
+    if (cap < 1) return cudaErrorInvalidConfiguration;
+    if (n_max > cap) n_max = cap;
+  }
+  if (n_max > steps_per_strip) n_max = steps_per_strip;
+  RingMapCache local;
+  RingMapCache* c = L.cache ? L.cache : &local;
+  long long best_n = n_max;
+  double best_cost = 1e300;
+  if (c->n_B == a.B && c->n_T == a.T && c->n_d == a.d && c->n_k == a.k && c->n_row0 == a.in_row0 && c->n_sm == L.sm_count) {
+    best_n = c->n;
+  } else {
+  const double warm = 0.5 * (a.k - 1) + 1.0;    // warm-up steps are cheaper than full ones; + fixed span overhead
+  for (long long n = n_max; n >= 1; --n) {
+    const long long sps = (steps_per_strip + n - 1) / n;
+    const long long total = sps * strips;
+    const long long waves = (total + ctas - 1) / ctas;
+    const double cost = (double)waves * ((double)n + warm);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_n = n; }
+  }
+    c->n_B = a.B; c->n_T = a.T; c->n_d = a.d; c->n_k = a.k; c->n_row0 = a.in_row0; c->n_sm = L.sm_count; c->n = best_n;
+  }
+  a.n = (int)best_n;
+  a.S = (long long)a.n * a.d;
+  a.spans_per_strip = (steps_per_strip + a.n - 1) / a.n;
+  a.total_spans = a.spans_per_strip * strips;
+  long long grid = a.total_spans < ctas ? a.total_spans : ctas;
+  grid *= n_grp;
+
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  CUtensorMap& in_map = *reinterpret_cast<CUtensorMap*>(c->in_map);
+  CUtensorMap& w_map = *reinterpret_cast<CUtensorMap*>(c->w_map);
+  if (c->in != L.in || c->in_rows != L.in_rows || c->in_stride != L.in_clip_stride_elems || c->B != a.B ||
+      c->mode != a.mode || c->d != a.d || c->S != a.S || c->in_row0 != a.in_row0) {
+    bool ok;
+    if (a.mode == 0) {
+      // dims (channel pair, r, j, clip): row (r, j) = j * S + r.  r spans the history prefix plus one group
+      // stride; j spans the clip.  The last group may run up to S + in_row0 rows past the clip (RB_SLACK_ROWS).
+      const uint64_t rext = (uint64_t)(a.in_row0 + a.S + a.d);
+      const uint64_t jext = (uint64_t)((L.in_rows + a.S - 1) / a.S);
+      ok = make_group_map(&in_map, L.in, rext, jext, (uint64_t)a.B, (uint64_t)a.S, (uint64_t)L.in_clip_stride_elems,
+                          (uint32_t)a.d, (uint32_t)a.G);
+    } else {
+      ok = make_plane_map(&in_map, L.in, 64, (uint64_t)L.in_rows, (uint64_t)a.B, (uint64_t)L.in_clip_stride_elems, 128);
+    }
+    if (!ok) return cudaErrorInvalidValue;
+    c->in = L.in; c->in_rows = L.in_rows; c->in_stride = L.in_clip_stride_elems; c->B = a.B;
+    c->mode = a.mode; c->d = a.d; c->S = a.S; c->in_row0 = a.in_row0;
+  }
+  if (c->w != L.wpacked || c->NS != a.NS) {
+    const uint64_t rows = (uint64_t)n_grp * a.NS * 32;
+    if (!make_plane_map(&w_map, L.wpacked, 64, rows, 1, rows * 64, 32)) return cudaErrorInvalidValue;
+    c->w = L.wpacked; c->NS = a.NS;
+  }
+
+  cudaError_t err;
+  static bool attr_set[2] = {false, false};
+  const void* fn = L.arch == 0 ? (const void*)ring_block_kernel<0> : (const void*)ring_block_kernel<1>;
+  if (!attr_set[L.arch]) {
+    err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (err != cudaSuccess) return err;
+    attr_set[L.arch] = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)((4 * RB_ESETS + 2) * 32));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = L.pdl ? 1 : 0;
+  if (L.arch == 0) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<0>, in_map, w_map, a);
+  else err = cudaLaunchKernelEx(&cfg, ring_block_kernel<1>, in_map, w_map, a);
+  if (err != cudaSuccess) return err;
+  return cudaGetLastError();
+}
+
+}  // namespace nasr

@@ -1,0 +1,78 @@
+// Declarations of the input-stationary ("accumulator ring") tcgen05 block kernel (ring_block.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+
+namespace nasr {
+
+constexpr int RB_TILE_BYTES = 16384;   // 128 rows x 128 B
+constexpr int RB_MAX_STAGES = 8;
+constexpr int RB_MAX_SLOTS = 16;       // 512 TMEM columns / 32
+// rows a mode-S launch may read past the end of the last clip of a plane (TMA bounds are per
+// dimension, see launch_ring_block); planes handed to the kernel carry this much slack
+constexpr long long RB_SLACK_ROWS = 32768;
+
+struct RingArgs {
+  void* out;
+  int out_fmt;
+  long long out_clip_stride, out_rows, out_row0;
+  long long in_row0;
+  int B;
+  long long T;
+  int k, d;
+  int mode;                // 0 = S (d < 128: G groups of d rows per tile), 1 = L (d >= 128: 128-row lanes of a period)
+  int G;                   // groups per tile (mode S)
+  int L;                   // lanes per period (mode L)
+  int n;                   // steps per span
+  long long S;             // mode S: rows between groups = n * d
+  long long NP;            // mode L: periods per clip
+  long long spans_per_strip, total_spans;
+  int NS;                  // accumulator slots = k + 1 (k taps + residual)
+  int NW;                  // weight blocks resident in shared memory (NS + wrap copy)
+  int stages;              // input tiles in flight
+  int tmem_cols;
+  const float* scale;
+  const float* shift;      // [B][ld_affine]
+  int ld_affine;
+  int grp, n_grp;          // GCN: output-channel group handled by this launch (16 gate channels each)
+  float slope, inv_sw, inv_sr;
+  const float* wout;       // [out_ch][32]
+  int out_ch, final_tanh;
+  unsigned int* sat_flag;
+  int dbg;                 // dev only (NASR_RB_DBG): 1 = epilogue drains without math/stores, 2 = no MMAs, 4 = no zeroing
+};
+
+struct RingMapCache {
+  alignas(64) unsigned char in_map[128];
+  alignas(64) unsigned char w_map[128];
+  const void* in = nullptr;
+  const void* w = nullptr;
+  long long in_rows = -1, in_stride = -1, S = -1, in_row0 = -1;
+  int B = -1, NS = -1, mode = -1, d = -1;
+  // span length chosen for the last launch shape
+  long long n_T = -1, n_row0 = -1, n = 0;
+  int n_B = -1, n_d = -1, n_k = -1, n_sm = -1;
+};
+
+struct RingLaunch {
+  RingMapCache* cache = nullptr;    // optional
+  const void* in;                   // SPLIT16 input plane (16-bit elements)
+  long long in_rows;                // rows per clip
+  long long in_clip_stride_elems;   // 16-bit elements between clips
+  const void* wpacked;              // device buffer from ring_pack_weights (one group)
+  int arch, sm_count;
+  bool pdl = false;                 // programmatic dependent launch (prologue overlaps the previous kernel's tail)
+  RingArgs a;
+};
+
+// eligibility: 32 -> 32 channels, k + 1 accumulator slots fit TMEM, and the tile rows are
+// well used for this dilation
+bool ring_eligible(int arch, int Cin, int C, int k, int d);
+// number of weight groups (launches per block): 1 for TCN, 2 for GCN
+int ring_groups(int arch);
+void ring_pack_weights(int arch, int grp, int k, const float* conv_w, const float* res_w, std::vector<uint16_t>& out,
+                       float* inv_sw, float* inv_sr);
+cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s);
+
+}  // namespace nasr

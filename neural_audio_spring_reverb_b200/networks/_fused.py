@@ -18,7 +18,9 @@ def _path_from_env() -> int:
         return _native.PATH_AUTO
     if v in ("fp32", "ffma", "1"):
         return _native.PATH_FP32
-    raise ValueError(f"NASR_PATH={v!r}: expected 'auto' or 'fp32'")
+    if v in ("tc", "gather", "2"):
+        return _native.PATH_TC_GATHER
+    raise ValueError(f"NASR_PATH={v!r}: expected 'auto', 'fp32' or 'tc'")
 
 
 class FusedNetMixin:

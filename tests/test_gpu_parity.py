@@ -241,19 +241,36 @@ TC_SHAPES = [
     ("TCN", 4, 1, 7), ("TCN", 4, 2, 3), ("TCN", 5, 5, 3), ("TCN", 4, 7, 10), ("TCN", 3, 31, 9),
     ("TCN", 4, 4, 100), ("TCN", 3, 6, 130), ("TCN", 3, 9, 127), ("TCN", 3, 3, 129),
     ("GCN", 4, 5, 4), ("GCN", 3, 9, 11), ("GCN", 3, 2, 200), ("GCN", 3, 15, 13),
+    # ring-kernel corners: 16 slots with every power-of-two dilation, d = 14 (126 of 128 rows), d = 196 (2 lanes)
+    ("TCN", 10, 15, 2), ("GCN", 10, 15, 2), ("TCN", 4, 3, 14), ("TCN", 3, 15, 196), ("GCN", 5, 14, 6),
 ]
 
 
+def _expected_paths(arch, n_blocks, k, dil, mode):
+    """Mirror of the engine's kernel choice (engine.cu path_of / ring_block.cu ring_eligible): 2 = accumulator-ring
+    kernel when k + 1 slots fit TMEM and >= 75 % of the tile rows are used, else 1 = tap-gather kernel."""
+    out = [0]
+    for i in range(1, n_blocks):
+        d = dil[i]
+        eff = ((128 // d) * d) / 128.0 if d < 128 else d / (128.0 * ((d + 127) // 128))
+        ring = mode == "auto" and k + 1 <= 16 and eff >= 0.75 and not (arch == "GCN" and i == n_blocks - 1)
+        out.append(2 if ring else 1)
+    return out
+
+
+@pytest.mark.parametrize("mode", ["auto", "tc"])
 @pytest.mark.parametrize("arch,n_blocks,k,g", TC_SHAPES)
-def test_tensor_core_path_shapes(arch, n_blocks, k, g):
+def test_tensor_core_path_shapes(arch, n_blocks, k, g, mode, monkeypatch):
     """Tap counts, odd / non-power-of-two dilations, both walk modes (d < 128 and d >= 128, partial
-    lanes) of the tcgen05 kernel, against the oracle; and the same net streamed in ragged chunks."""
+    lanes) of both tcgen05 kernels (NASR_PATH=auto: accumulator ring where eligible; tc: tap gather
+    only), against the oracle; and the same net streamed in ragged chunks."""
     import neural_audio_spring_reverb_b200 as N
+    monkeypatch.setenv("NASR_PATH", mode)
     cfg = dict(arch=arch, n_blocks=n_blocks, n_channels=32, kernel_size=k, dilation_growth=g, cond_dim=2)
     sd = O.build_state(arch, n_blocks, 32, k, 2, seed=k * 31 + g)
     dil = [g ** i for i in range(n_blocks)]
     m = build_model(cfg, sd, DEV)
-    assert [m._engine().block_path(i) for i in range(n_blocks)] == [0] + [1] * (n_blocks - 1)
+    assert [m._engine().block_path(i) for i in range(n_blocks)] == _expected_paths(arch, n_blocks, k, dil, mode)
     rf = O.receptive_field(k, dil) if k > 1 else 1
     T = min(max(3 * rf, 9000), 60000) + 37
     x = O.make_input(2, 1, T)

@@ -1,0 +1,21 @@
+"""Dev: per-block time of the ring kernel on cfg2 under debug switches (env NASR_RB_DBG, NASR_LIB)."""
+import os, sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import torch
+from oracle import nasr_oracle as O
+from util import build_model
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 480000
+cname = sys.argv[3] if len(sys.argv) > 3 else "cfg2"
+cfg = O.CONFIGS[cname]; sd = O.config_state(cname)
+m = build_model(cfg, sd, "cuda:0")
+x = torch.rand(B, 1, T, device="cuda:0") * 2 - 1
+c = torch.full((B, 2), 0.5, device="cuda:0")
+y = m(x, c); torch.cuda.synchronize()
+eng = m._engine(); yd = torch.empty_like(y); best = None
+for _ in range(5):
+    ms = eng.forward_profiled(x.data_ptr(), yd.data_ptr(), B, T)
+    best = ms if best is None else [min(a, b) for a, b in zip(best, ms)]
+print(f"{cname} B={B} T={T} dbg={os.environ.get('NASR_RB_DBG')} lib={os.path.basename(os.environ.get('NASR_LIB','default'))} blocks(us)={[round(v*1e3,1) for v in best]}", flush=True)
