@@ -86,4 +86,27 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// Warp-cooperative store of 32 consecutive plane rows (lane = row) of NCHK 16-byte chunks each.
+// A thread that stores its own row 16 bytes at a time touches 32 different lines per instruction
+// (32 LSU wavefronts, half-filled sectors); staged through a warp-private XOR-swizzled tile the
+// same bytes leave as whole rows, NCHK lanes per row.  stage: 32 * NCHK * 16 bytes, 16-byte aligned.
+template <int NCHK>
+__device__ __forceinline__ void warp_store_rows(uint8_t* stage, const uint4 (&ch)[NCHK], int lane, uint8_t* dst_row0,
+                                                int nvalid) {
+  constexpr int RPI = (NCHK >= 32) ? 1 : 32 / NCHK;   // rows per store instruction
+  const int wsw = (NCHK == 4) ? ((lane >> 1) & 3) : (lane & 7);
+#pragma unroll
+  for (int q = 0; q < NCHK; ++q) *reinterpret_cast<uint4*>(stage + lane * (NCHK * 16) + ((q ^ wsw) * 16)) = ch[q];
+  __syncwarp();
+  const int my_c = lane % NCHK, my_r = lane / NCHK;
+#pragma unroll
+  for (int q = 0; q < 32 / RPI; ++q) {
+    const int rl = RPI * q + my_r;
+    const int rsw = (NCHK == 4) ? ((rl >> 1) & 3) : (rl & 7);
+    const uint4 val = *reinterpret_cast<const uint4*>(stage + rl * (NCHK * 16) + ((my_c ^ rsw) * 16));
+    if (rl < nvalid) *reinterpret_cast<uint4*>(dst_row0 + (long long)rl * (NCHK * 16) + my_c * 16) = val;
+  }
+  __syncwarp();
+}
+
 }  // namespace nasr

@@ -813,6 +813,11 @@ int64_t nasr_receptive_field(const nasr_engine* e) {
   return rf;
 }
 
+// dev only (not in the public header): timeline stamps of the last ring-kernel launch
+__attribute__((visibility("default"))) int nasr_debug_ring_stamps(unsigned long long* host, int max_ctas) {
+  return ring_debug_stamps(host, max_ctas);
+}
+
 int64_t nasr_launch_count(const nasr_engine* e) { return e ? e->launches : 0; }
 
 int nasr_block_path(const nasr_engine* e, int block) {

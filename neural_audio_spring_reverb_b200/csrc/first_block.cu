@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(FB_THREADS, ((ARCH == 1 ? 2 * C : C) > 32 ? 2 
   extern __shared__ __align__(16) float fsm[];
   const int Cin = a.Cin, k = a.k, d = a.d;
   const int H = (k - 1) * d;
-  float* ws = fsm;                         // [k][Cin][W]   original channel order
+  float* stg = fsm;                        // [4 warps][32 rows][C] row staging for the coalesced stores
+  float* ws = stg + (FB_THREADS / 32) * 32 * C;   // [k][Cin][W]   original channel order
   float* rs = ws + k * Cin * W;            // [Cin][C]
   float* os = rs + Cin * C;                // [out_ch][C]   (FMT_FINAL)
   float* ss = os + (a.out_fmt == FMT_FINAL ? a.out_ch * C : 0);   // [2][W] scale, shift of the current clip
@@ -107,42 +108,50 @@ __global__ void __launch_bounds__(FB_THREADS, ((ARCH == 1 ? 2 * C : C) > 32 ? 2 
 #pragma unroll
         for (int c = 0; c < C; ++c) o[c] = fmaf(xv, rs[ci * C + c], o[c]);
       }
-      if (t < a.T) {
-        if (a.out_fmt == FMT_SPLIT16) {
-          __half* dst = (__half*)a.out + (long long)b * a.out_clip_stride + (a.out_row0 + t) * (2LL * a.Coutp);
-          uint32_t hi[C / 2], lo[C / 2];
-          float vmax = 0.f;
+      // rows of this warp in this half: t0 + 128 * half + 32 * warp + lane, consecutive in the plane
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const long long tw = t0 + 128 * half + 32 * warp;
+      long long left = a.T - tw;
+      const int nvalid = left > 32 ? 32 : (left < 0 ? 0 : (int)left);
+      uint8_t* stage = reinterpret_cast<uint8_t*>(stg) + (size_t)warp * (32 * C * 4);
+      if (a.out_fmt == FMT_SPLIT16) {
+        uint32_t hi[C / 2], lo[C / 2];
+        float vmax = 0.f;
 #pragma unroll
-          for (int c = 0; c < C; ++c) vmax = fmaxf(vmax, fabsf(o[c]));
-          if (vmax > 65504.f) *a.sat_flag = 1u;
+        for (int c = 0; c < C; ++c) vmax = fmaxf(vmax, fabsf(o[c]));
+        if (vmax > 65504.f && t < a.T) *a.sat_flag = 1u;
 #pragma unroll
-          for (int c = 0; c < C; c += 2) {
-            const float x0 = fminf(fmaxf(o[c], -65504.f), 65504.f), x1 = fminf(fmaxf(o[c + 1], -65504.f), 65504.f);
-            const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-            const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-            hi[c >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            lo[c >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-          }
-          uint4* d4 = reinterpret_cast<uint4*>(dst);
-          uint4* l4 = reinterpret_cast<uint4*>(dst + a.Coutp);
+        for (int c = 0; c < C; c += 2) {
+          const float x0 = fminf(fmaxf(o[c], -65504.f), 65504.f), x1 = fminf(fmaxf(o[c + 1], -65504.f), 65504.f);
+          const __half2 h = __floats2half2_rn(x0, x1);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+          hi[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          lo[c >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        uint4 ch[C / 4];   // row = C x fp16 hi then C x fp16 lo
 #pragma unroll
-          for (int v = 0; v < C / 8; ++v) {
-            d4[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-            l4[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
-          }
-        } else if (a.out_fmt == FMT_CL) {
-          float4* dst = reinterpret_cast<float4*>((float*)a.out + (long long)b * a.out_clip_stride +
-                                                  (a.out_row0 + t) * (long long)a.Coutp);
+        for (int v = 0; v < C / 8; ++v) {
+          ch[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+          ch[C / 8 + v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+        }
+        uint8_t* dst = reinterpret_cast<uint8_t*>((__half*)a.out + (long long)b * a.out_clip_stride) + (a.out_row0 + tw) * (4LL * C);
+        warp_store_rows<C / 4>(stage, ch, lane, dst, nvalid);
+      } else if (a.out_fmt == FMT_CL) {
+        uint4 ch[C / 4];
 #pragma unroll
-          for (int v = 0; v < C / 4; ++v) dst[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
-        } else {  // FMT_FINAL
-          for (int oc = 0; oc < a.out_ch; ++oc) {
-            float y = 0.f;
+        for (int v = 0; v < C / 4; ++v)
+          ch[v] = make_uint4(__float_as_uint(o[4 * v]), __float_as_uint(o[4 * v + 1]), __float_as_uint(o[4 * v + 2]),
+                             __float_as_uint(o[4 * v + 3]));
+        uint8_t* dst = reinterpret_cast<uint8_t*>((float*)a.out + (long long)b * a.out_clip_stride) + (a.out_row0 + tw) * (4LL * C);
+        warp_store_rows<C / 4>(stage, ch, lane, dst, nvalid);
+      } else if (t < a.T) {  // FMT_FINAL
+        for (int oc = 0; oc < a.out_ch; ++oc) {
+          float y = 0.f;
 #pragma unroll
-            for (int c = 0; c < C; ++c) y = fmaf(o[c], os[oc * C + c], y);
-            if (a.final_tanh) y = tanhf(y);
-            ((float*)a.out)[(long long)b * a.out_clip_stride + (long long)oc * a.out_rows + a.out_row0 + t] = y;
-          }
+          for (int c = 0; c < C; ++c) y = fmaf(o[c], os[oc * C + c], y);
+          if (a.final_tanh) y = tanhf(y);
+          ((float*)a.out)[(long long)b * a.out_clip_stride + (long long)oc * a.out_rows + a.out_row0 + t] = y;
         }
       }
     }
@@ -153,7 +162,7 @@ template <int ARCH, int C>
 static cudaError_t launch_fb(const BlockArgs& a, const float* w0, int sm_count, cudaStream_t s) {
   constexpr int W = ARCH == 1 ? 2 * C : C;
   const int H = (a.k - 1) * a.d;
-  const size_t smem = sizeof(float) * ((size_t)a.k * a.Cin * W + (size_t)a.Cin * C +
+  const size_t smem = sizeof(float) * ((size_t)(FB_THREADS / 32) * 32 * C + (size_t)a.k * a.Cin * W + (size_t)a.Cin * C +
                                        (a.out_fmt == FMT_FINAL ? (size_t)a.out_ch * C : 0) + 2 * (size_t)W +
                                        (size_t)a.Cin * (H + FB_ROWS));
   if (smem > 100 * 1024) return cudaErrorNotSupported;

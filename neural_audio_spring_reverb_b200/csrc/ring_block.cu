@@ -90,6 +90,14 @@ __device__ __forceinline__ float rb_sigmoid(float x) {
   return e > 1e30f ? 0.0f : __fdividef(1.0f, 1.0f + e);
 }
 
+__device__ __forceinline__ void rb_stamp(const RingArgs& a, int slot) {
+  if (a.dbg_buf) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.dbg_buf[(size_t)blockIdx.x * 16 + slot] = t;
+  }
+}
+
 // one span = n consecutive steps of one strip (clip b, lane l)
 struct Span {
   int b, l, nsteps;
@@ -139,6 +147,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
   const int km1 = a.k - 1, NS = a.NS;
 
   if (threadIdx.x == 0) {
+    rb_stamp(a, 0);
     for (int i = 0; i < RB_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&done[0], 1);
     mbar_init(&done[1], 1);
@@ -154,6 +163,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (threadIdx.x == 0) rb_stamp(a, 1);
   // let the next kernel of the stream get scheduled as CTAs of this one retire (its own
   // griddepcontrol.wait keeps it from touching our output before we are completely done)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -172,6 +182,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         tma_load_3d(wsm + (size_t)p * 4096, &w_map, wfull, 0, (grp * NS + (p >= NS ? p - NS : p)) * 32, 0);
       // everything above is independent of the previous kernel in the stream
       asm volatile("griddepcontrol.wait;" ::: "memory");
+      rb_stamp(a, 2);
       const uint32_t tile_bytes = a.mode == 0 ? (uint32_t)(a.G * a.d * 128) : (uint32_t)RB_TILE_BYTES;
       int st = 0;
       uint32_t empty_phase = ~0u;
@@ -222,6 +233,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
       const int h0 = nchunk == 2 ? (NS + 1) / 2 : NS;
       mbar_wait(wfull, 0);
       tc_fence_after();
+      rb_stamp(a, 3);
       int st = 0;
       uint32_t full_phase = 0, drain_phase = 0, e = 0;
       bool pending = false;
@@ -242,6 +254,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           mbar_wait(&full[st], (full_phase >> st) & 1u);
           full_phase ^= 1u << st;
           tc_fence_after();
+          if (e == 0 && i == -km1) rb_stamp(a, 4);
           const uint32_t a_lo = ring_lo + (uint32_t)st * (RB_TILE_BYTES >> 4);
           const int len = i + a.k;                  // blocks -i .. k-1  ->  slots 0 .. len-1
           const int nf = len - 1;                   // slots already started
@@ -266,6 +279,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         // ---- steady state: every block, fixed chunks of the ring; slot (i + b) mod NS <- block b.  The two
         //      slots that start at step i, (i-2) and (i-1) mod NS, were read AND zeroed by epilogue(i-1), so
         //      every instruction accumulates; the chunk that holds them waits for that drain. ----
+        if (e == 1) rb_stamp(a, 5);
         int islot = 1 % NS;
         for (int i = 1; i < s.nsteps; ++i) {
           mbar_wait(&full[st], (full_phase >> st) & 1u);
@@ -309,6 +323,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           islot = islot + 1 == NS ? 0 : islot + 1;
         }
       }
+      rb_stamp(a, 6);
     }
     __syncwarp();
   } else {
@@ -392,6 +407,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         const int cslot = i % NS, rslot = (i + NS - 1) % NS;
         mbar_wait(&done[e & 1u], (e >> 1) & 1u);
         tc_fence_after();
+        if (e == 0 && threadIdx.x == 0) rb_stamp(a, 7);
         float o[NO];
         if (a.dbg & 1) {   // dev: drain only
           uint32_t u[32];
@@ -512,10 +528,12 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         __syncwarp();
       }
     }
+    if (threadIdx.x == 0) rb_stamp(a, 8);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) rb_stamp(a, 9);
   if (warp == PRODUCER_WARP) tmem_dealloc(tmem, (uint32_t)a.tmem_cols);
 }
 
@@ -597,6 +615,16 @@ static bool make_group_map(CUtensorMap* map, const void* base, uint64_t rext, ui
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static unsigned long long* g_dbg_buf = nullptr;
+// dev: copy the stamps of the last launch (NASR_RB_DBG & 8) to the host; returns number of CTAs covered
+int ring_debug_stamps(unsigned long long* host, int max_ctas) {
+  if (!g_dbg_buf) return 0;
+  cudaDeviceSynchronize();
+  const int n = max_ctas < 1024 ? max_ctas : 1024;
+  cudaMemcpy(host, g_dbg_buf, (size_t)n * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return n;
+}
+
 cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   RingArgs a = L.a;
   if (a.B <= 0 || a.T <= 0) return cudaSuccess;
@@ -604,6 +632,14 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("NASR_RB_DBG"); dbg = e ? atoi(e) : 0; }
     a.dbg = dbg;
+    a.dbg_buf = nullptr;
+    if (dbg & 8) {   // dev: per-CTA %globaltimer stamps, read back with ring_debug_stamps()
+      static unsigned long long* buf = nullptr;
+      if (!buf) { cudaMalloc(&buf, 1024 * 16 * sizeof(unsigned long long)); }
+      cudaMemsetAsync(buf, 0, 1024 * 16 * sizeof(unsigned long long), s);
+      a.dbg_buf = buf;
+      g_dbg_buf = buf;
+    }
   }
   const int n_grp = ring_groups(L.arch);
   a.n_grp = n_grp;

@@ -40,6 +40,7 @@ struct RingArgs {
   const float* wout;       // [out_ch][32]
   int out_ch, final_tanh;
   unsigned int* sat_flag;
+  unsigned long long* dbg_buf;   // dev only: per-CTA timeline stamps
   int dbg;                 // dev only (NASR_RB_DBG): 1 = epilogue drains without math/stores, 2 = no MMAs, 4 = no zeroing
 };
 
@@ -74,5 +75,6 @@ int ring_groups(int arch);
 void ring_pack_weights(int arch, int grp, int k, const float* conv_w, const float* res_w, std::vector<uint16_t>& out,
                        float* inv_sw, float* inv_sr);
 cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s);
+int ring_debug_stamps(unsigned long long* host, int max_ctas);
 
 }  // namespace nasr
