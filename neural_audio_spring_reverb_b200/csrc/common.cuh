@@ -1,6 +1,7 @@
 // Shared declarations for the libnasr_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace nasr {
@@ -8,10 +9,17 @@ namespace nasr {
 // Activation plane formats.
 //   NCT     : fp32 [B][C][rows]            (reference layout; x, y and single-block I/O)
 //   CL      : fp32 [B][rows][Cp]           (channels-last, Cp = C rounded up to 4)
-//   SPLIT16 : [B][rows][2*Cp] 16-bit       (per row: Cp x fp16 "hi" then Cp x bf16 "lo",
-//                                           value = hi + lo; same bytes as CL fp32;
+//   SPLIT16 : [B][rows][2*Cp] 16-bit       (per row: Cp x fp16 "hi" then Cp x fp16 "lo",
+//                                           value * kActScale = hi + lo; same bytes as CL fp32;
 //                                           it is the operand format of the tcgen05 kernel)
 //   FINAL   : out_net (1x1, C -> out_ch) [+ tanh] fused; written as NCT fp32
+// SPLIT16 planes (and the Toeplitz tile of block 0) hold value * kActScale: fp16 lo parts of O(1) activations
+// would otherwise be subnormal (absolute precision 6e-8 instead of 22 bits) and quiet signals would lose
+// accuracy. 2^6 keeps the clamp at |value| > 1023 (shipped checkpoints peak near 40 for full-scale input);
+// consumers fold 1 / kActScale into their accumulator scales.
+constexpr float kActScale = 64.0f;
+constexpr float kActInv = 1.0f / 64.0f;
+
 enum PlaneFmt : int { FMT_NCT = 0, FMT_CL = 1, FMT_SPLIT16 = 2, FMT_FINAL = 3 };
 
 // One fused block launch: causal dilated conv -> folded bias/BN/FiLM affine ->
@@ -84,6 +92,27 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ---- packed fp32x2 epilogue pieces shared by the tensor-core kernels (sm_100 FFMA2 / FMUL2 / FADD2) ----
+// PReLU with one slope a (tcn.py:65): y > 0 ? y : a*y  ==  max(y, a*y) for a <= 1, min(y, a*y) for a > 1 (exact).
+__device__ __forceinline__ float2 prelu2(float2 y, float2 slope2, bool slope_le1) {
+  const float2 sy = __fmul2_rn(y, slope2);
+  return slope_le1 ? make_float2(fmaxf(y.x, sy.x), fmaxf(y.y, sy.y)) : make_float2(fminf(y.x, sy.x), fminf(y.y, sy.y));
+}
+// value pair -> fp16 hi pair + fp16 lo pair (value = hi + lo to >= 22 bits); no range clamp (see split16_pair_clamped)
+__device__ __forceinline__ void split16_pair(float2 o, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(o.x, o.y);
+  const float2 hf = __half22float2(h);
+  const float2 d = __fadd2_rn(o, make_float2(-hf.x, -hf.y));
+  const __half2 l = __floats2half2_rn(d.x, d.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void split16_pair_clamped(float2 o, uint32_t& hi, uint32_t& lo) {
+  o.x = fminf(fmaxf(o.x, -65504.f), 65504.f);
+  o.y = fminf(fmaxf(o.y, -65504.f), 65504.f);
+  split16_pair(o, hi, lo);
 }
 
 // Warp-cooperative store of 32 consecutive plane rows (lane = row) of NCHK 16-byte chunks each.

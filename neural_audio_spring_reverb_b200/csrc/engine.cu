@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "tc_block.cuh"
 #include "ring_block.cuh"
+#include "toep_block.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -36,6 +37,9 @@ struct BlockState {
   float* w0 = nullptr;                       // first block: conv weights [k][Cin][W], original order
   uint16_t* wtc = nullptr;                   // tcgen05 paths: split-fp16 weight tiles (tc_pack_weights / ring_pack_weights)
   float inv_sw = 1.f, inv_sr = 1.f;
+  uint16_t* wtoep = nullptr;                 // first block on the tensor cores (toep_pack_weights)
+  int toep_kp = 0;
+  float toep_inv_sw = 1.f, toep_inv_sr = 1.f;
 };
 
 }  // namespace
@@ -47,6 +51,7 @@ struct nasr_engine {
   std::vector<BlockState> blocks;
   std::vector<TcMapCache> tc_cache;   // per block: last TMA descriptors
   std::vector<RingMapCache> ring_cache;
+  ToepMapCache toep_cache;
   float* wout = nullptr;  // [out_ch][Cp]
   FoldArgs* fold_dev = nullptr;
   int condCap = 0, condB = 0;
@@ -172,6 +177,8 @@ void free_block(BlockState& b) {
   b.wtc = nullptr;
   if (b.w0) cudaFree(b.w0);
   b.w0 = nullptr;
+  if (b.wtoep) cudaFree(b.wtoep);
+  b.wtoep = nullptr;
 }
 
 // tc = false plans the all-fp32 chain (generic kernels, CL planes) for this call
@@ -206,7 +213,8 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
     TcArgs& t = L.a;
     t.out = a.out; t.out_fmt = a.out_fmt; t.out_clip_stride = a.out_clip_stride; t.out_rows = a.out_rows;
     t.out_row0 = a.out_row0; t.in_row0 = a.in_row0; t.B = a.B; t.T = a.T; t.k = a.k; t.d = a.d;
-    t.scale = a.scale; t.shift = a.shift; t.slope = a.slope; t.inv_sw = bs.inv_sw; t.inv_sr = bs.inv_sr;
+    t.scale = a.scale; t.shift = a.shift; t.slope = a.slope;
+    t.inv_sw = bs.inv_sw * kActInv; t.inv_sr = bs.inv_sr * kActInv;   // the input plane holds value * kActScale
     t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_flag;
     err = launch_tc_block(L, s);
   } else if (allow_tc && tc_chain && bs.path == 2) {
@@ -217,12 +225,26 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
     RingArgs& t = L.a;
     t.out = a.out; t.out_fmt = a.out_fmt; t.out_clip_stride = a.out_clip_stride; t.out_rows = a.out_rows;
     t.out_row0 = a.out_row0; t.in_row0 = a.in_row0; t.B = a.B; t.T = a.T; t.k = a.k; t.d = a.d;
-    t.scale = a.scale; t.shift = a.shift; t.ld_affine = bs.Wp; t.slope = a.slope; t.inv_sw = bs.inv_sw; t.inv_sr = bs.inv_sr;
+    t.scale = a.scale; t.shift = a.shift; t.ld_affine = bs.Wp; t.slope = a.slope;
+    t.inv_sw = bs.inv_sw * kActInv; t.inv_sr = bs.inv_sr * kActInv;   // the input plane holds value * kActScale
     t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_flag;
     err = launch_ring_block(L, s);
   } else {
     err = cudaErrorNotSupported;
-    if (bs.w0 && allow_tc) err = launch_first_block(a, bs.w0, e->sm_count, s);
+    if (bs.wtoep && allow_tc && tc_chain && a.in_fmt == FMT_NCT && toep_eligible(a.arch, a.Cin, a.Cout, a.k, a.out_fmt)) {
+      ToepLaunch L{};
+      L.cache = &e->toep_cache; L.wpacked = bs.wtoep; L.arch = a.arch; L.sm_count = e->sm_count; L.Kp = bs.toep_kp;
+      L.pdl = e->pdl;
+      ToepArgs& t = L.a;
+      t.x = (const float*)a.in; t.in_clip_stride = a.in_clip_stride; t.in_rows = a.in_rows; t.in_row0 = a.in_row0;
+      t.out = a.out; t.out_fmt = a.out_fmt; t.out_clip_stride = a.out_clip_stride; t.out_row0 = a.out_row0;
+      t.B = a.B; t.T = a.T; t.Cin = a.Cin; t.k = a.k; t.d = a.d;
+      t.scale = a.scale; t.shift = a.shift; t.ld_affine = bs.Wp; t.slope = a.slope;
+      t.inv_sw = bs.toep_inv_sw * kActInv; t.inv_sr = bs.toep_inv_sr * kActInv;   // the Toeplitz tile holds x * kActScale
+      t.sat_flag = e->sat_flag;
+      err = launch_toep_block(L, s);
+    }
+    if (err == cudaErrorNotSupported && bs.w0 && allow_tc) err = launch_first_block(a, bs.w0, e->sm_count, s);
     if (err == cudaErrorNotSupported) err = launch_generic_block(a, e->sm_count, s);
   }
   if (err != cudaSuccess)
@@ -389,6 +411,11 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
         for (int ci = 0; ci < b.Cin; ++ci)
           for (int j = 0; j < k; ++j) h_w0[((size_t)j * b.Cin + ci) * b.W + co] = conv_w[((size_t)co * b.Cin + ci) * k + j];
       up(&b.w0, h_w0);
+      if (desc->path != NASR_PATH_FP32 && toep_eligible(desc->arch, b.Cin, C, k, FMT_SPLIT16)) {
+        std::vector<uint16_t> h_wt;
+        toep_pack_weights(desc->arch, b.Cin, k, conv_w, res_w, h_wt, &b.toep_inv_sw, &b.toep_inv_sr, &b.toep_kp);
+        up(&b.wtoep, h_wt);
+      }
     }
     if (b.path == 1) {
       std::vector<uint16_t> h_wtc;

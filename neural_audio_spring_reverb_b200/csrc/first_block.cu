@@ -118,7 +118,10 @@ __global__ void __launch_bounds__(FB_THREADS, ((ARCH == 1 ? 2 * C : C) > 32 ? 2 
         uint32_t hi[C / 2], lo[C / 2];
         float vmax = 0.f;
 #pragma unroll
-        for (int c = 0; c < C; ++c) vmax = fmaxf(vmax, fabsf(o[c]));
+        for (int c = 0; c < C; ++c) {
+          o[c] *= kActScale;
+          vmax = fmaxf(vmax, fabsf(o[c]));
+        }
         if (vmax > 65504.f && t < a.T) *a.sat_flag = 1u;
 #pragma unroll
         for (int c = 0; c < C; c += 2) {

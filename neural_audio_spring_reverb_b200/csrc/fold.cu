@@ -14,6 +14,8 @@ namespace nasr {
 // Without FiLM (TCN with cond_dim == 0, tcn.py:63-64): scale = 1, shift = bias.
 // Computed in fp64 and rounded once.
 __global__ void fold_kernel(const FoldArgs* __restrict__ blocks, const float* __restrict__ cond) {
+  // the first block kernel may start its prologue now; it waits (griddepcontrol.wait) before reading scale/shift
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const FoldArgs f = blocks[blockIdx.x];
   const int b = blockIdx.y;
   for (int w = threadIdx.x; w < f.W; w += blockDim.x) {

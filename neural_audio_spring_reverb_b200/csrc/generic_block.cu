@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(512, 1) generic_block_kernel(const BlockArgs a
         float v = 0.f;
         if (ok) {
           const __half* p = src + row * (2LL * a.Cinp) + c0 + ci;
-          v = __half2float(p[0]) + __half2float(p[a.Cinp]);
+          v = (__half2float(p[0]) + __half2float(p[a.Cinp])) * kActInv;
         }
         xs[r * XS + ci] = v;
       }
@@ -284,8 +284,9 @@ __global__ void __launch_bounds__(512, 1) generic_block_kernel(const BlockArgs a
             for (int n = 0; n < NCO; n += 4) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                if (fabsf(o[n + q]) > 65504.f) *a.sat_flag = 1u;
-                const float xv = fminf(fmaxf(o[n + q], -65504.f), 65504.f);
+                const float sv = o[n + q] * kActScale;
+                if (fabsf(sv) > 65504.f) *a.sat_flag = 1u;
+                const float xv = fminf(fmaxf(sv, -65504.f), 65504.f);
                 hi[q] = __float2half_rn(xv);
                 lo[q] = __float2half_rn(xv - __half2float(hi[q]));
               }

@@ -371,16 +371,19 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     if (ARCH == 0) cbyte = my_c * 16;
     else if (a.out_fmt == FMT_SPLIT16) cbyte = (my_c < 2 ? 0 : 64) + grp * 32 + (my_c & 1) * 16;
     else cbyte = grp * 64 + my_c * 16;
-    const float slope = a.slope, inv_sr = a.inv_sr;
+    const float oscale = a.out_fmt == FMT_SPLIT16 ? kActScale : 1.0f;
+    const float inv_sr = a.inv_sr * oscale;
+    const float2 slope2 = make_float2(a.slope, a.slope), isr2 = make_float2(inv_sr, inv_sr);
+    const bool slope_le1 = a.slope <= 1.0f;
     uint32_t e = 0;
     Span s;
     for (long long sp = sp0; s.set(a, sp); sp += sp_stride) {
       const float* sc = a.scale + (long long)s.b * a.ld_affine;
       const float* sh = a.shift + (long long)s.b * a.ld_affine;
       __syncwarp();
-      if (ARCH == 0) {
-        aff[lane] = __ldg(sc + lane) * a.inv_sw;
-        aff[32 + lane] = __ldg(sh + lane);
+      if (ARCH == 0) {   // PReLU is positively homogeneous: the output scale of a SPLIT16 plane folds into the affine
+        aff[lane] = __ldg(sc + lane) * a.inv_sw * oscale;
+        aff[32 + lane] = __ldg(sh + lane) * oscale;
       } else {   // lanes 0..15: tanh half of this group, 16..31: sigmoid half (one padded width = 32 further)
         const int src = (lane < 16) ? grp * 16 + lane : 32 + grp * 16 + (lane - 16);
         aff[lane] = __ldg(sc + src) * a.inv_sw;
@@ -439,13 +442,15 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           for (int c = 0; c < 32; c += 4) {
             const float4 s4 = *reinterpret_cast<const float4*>(aff + c);
             const float4 h4 = *reinterpret_cast<const float4*>(aff + 32 + c);
-            const float ss[4] = {s4.x, s4.y, s4.z, s4.w}, hh[4] = {h4.x, h4.y, h4.z, h4.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float y = fmaf(__uint_as_float(u[c + q]), ss[q], hh[q]);
-              const float p = fmaxf(y, 0.f) + slope * fminf(y, 0.f);
-              o[c + q] = fmaf(__uint_as_float(v[c + q]), inv_sr, p);
-            }
+            const float2 y0 = __ffma2_rn(make_float2(__uint_as_float(u[c]), __uint_as_float(u[c + 1])), make_float2(s4.x, s4.y),
+                                         make_float2(h4.x, h4.y));
+            const float2 y1 = __ffma2_rn(make_float2(__uint_as_float(u[c + 2]), __uint_as_float(u[c + 3])),
+                                         make_float2(s4.z, s4.w), make_float2(h4.z, h4.w));
+            const float2 r0 = __ffma2_rn(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), isr2,
+                                         prelu2(y0, slope2, slope_le1));
+            const float2 r1 = __ffma2_rn(make_float2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])), isr2,
+                                         prelu2(y1, slope2, slope_le1));
+            o[c] = r0.x; o[c + 1] = r0.y; o[c + 2] = r1.x; o[c + 3] = r1.y;
           }
         } else {
           uint32_t u[32], v[16];
@@ -462,7 +467,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           for (int c = 0; c < 16; ++c) {
             const float yt = fmaf(__uint_as_float(u[c]), aff[c], aff[32 + c]);
             const float ys = fmaf(__uint_as_float(u[16 + c]), aff[16 + c], aff[48 + c]);
-            o[c] = fmaf(__uint_as_float(v[c]), inv_sr, rb_tanh(yt) * rb_sigmoid(ys));
+            o[c] = fmaf(__uint_as_float(v[c]), inv_sr, rb_tanh(yt) * rb_sigmoid(ys) * oscale);
           }
         }
 
@@ -488,16 +493,14 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           uint32_t hi[NO / 2], lo[NO / 2];
           float vmax = 0.f;
 #pragma unroll
-          for (int c = 0; c < NO; ++c) vmax = fmaxf(vmax, fabsf(o[c]));
-          if (vmax > 65504.f && ok && t0 + off < a.T) *a.sat_flag = 1u;
+          for (int c = 0; c < NO; c += 2) vmax = fmaxf(vmax, fmaxf(fabsf(o[c]), fabsf(o[c + 1])));
+          if (vmax > 65504.f) {   // beyond the fp16 range of the SPLIT16 planes: clamp and flag (rare)
+            if (ok && t0 + off < a.T) *a.sat_flag = 1u;
 #pragma unroll
-          for (int c = 0; c < NO; c += 2) {
-            const float x0 = fminf(fmaxf(o[c], -65504.f), 65504.f), x1 = fminf(fmaxf(o[c + 1], -65504.f), 65504.f);
-            const __half2 h = __floats2half2_rn(x0, x1);
-            const float2 hf = __half22float2(h);
-            const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-            hi[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-            lo[c >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+            for (int c = 0; c < NO; c += 2) split16_pair_clamped(make_float2(o[c], o[c + 1]), hi[c >> 1], lo[c >> 1]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < NO; c += 2) split16_pair(make_float2(o[c], o[c + 1]), hi[c >> 1], lo[c >> 1]);
           }
 #pragma unroll
           for (int q = 0; q < NCH / 2; ++q) {

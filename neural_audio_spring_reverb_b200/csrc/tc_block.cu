@@ -415,7 +415,10 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
             uint32_t hi[16], lo[16];
             float vmax = 0.f;
 #pragma unroll
-            for (int c = 0; c < C; ++c) vmax = fmaxf(vmax, fabsf(o[c]));
+            for (int c = 0; c < C; ++c) {
+              o[c] *= kActScale;
+              vmax = fmaxf(vmax, fabsf(o[c]));
+            }
             if (vmax > 65504.f) *a.sat_flag = 1u;
 #pragma unroll
             for (int c = 0; c < C; c += 2) {

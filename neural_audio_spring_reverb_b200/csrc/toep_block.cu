@@ -1,0 +1,481 @@
+// First block of the network (Cin = in_ch <= 4, C = 32) on the tensor cores (sm_100a).
+//
+// Same arithmetic as first_block.cu / generic_block.cu (reference src/nasr/networks/tcn.py:73-86,
+// gcn.py:53-61, custom_layers.py:32-42,85-88).  With Cin = 1 the causal conv is a [T x k] Toeplitz
+// matrix times a [k x W] weight matrix: the builder warps write that Toeplitz tile (128 samples x
+// Kp = 16 or 32 columns, column kappa = ci*k + j holds x[ci, t - (k-1-j)*d]) straight into shared
+// memory as a K-major SWIZZLE_128B operand, split into fp16 hi + fp16 lo like the SPLIT16 planes
+// (row = [hi 0..Kp-1 | lo 0..Kp-1]), and three small MMAs per tile (hi*hi, hi*lo, lo*hi; N = W + 32)
+// produce the conv and - through 32 extra weight rows that are non-zero only in the zero-shift
+// column - the 1x1 residual.  The 480 FMAs per sample of the CUDA-core kernel disappear; what is
+// left is the epilogue (affine, PReLU | tanh*sigmoid, + residual, SPLIT16 split, coalesced row
+// stores), spread over 12 epilogue warps so that its latency is hidden.
+#include "common.cuh"
+#include "sm100.cuh"
+#include "toep_block.cuh"
+#include <cuda_fp16.h>
+#include <cmath>
+
+namespace nasr {
+using namespace sm100;
+
+namespace {
+
+constexpr int TP_STAGES = 4;          // A tiles in flight
+constexpr int TP_SLOTS = 4;           // TMEM accumulator slots of 128 columns
+constexpr int TP_ESETS = 3;           // epilogue warp sets (4 warps each)
+constexpr int TP_BUILD_WARPS = 4;
+constexpr int TP_PREFETCH = 4;        // tiles (of this CTA) the x prefetch runs ahead
+constexpr int TP_EPI_WARPS = 4 * TP_ESETS;
+constexpr int TP_THREADS = (TP_BUILD_WARPS + TP_EPI_WARPS) * 32;   // 16 warps: 128 registers each
+
+__device__ __forceinline__ void tp_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ float tp_tanh(float x) {
+  const float e = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+__device__ __forceinline__ float tp_sigmoid(float x) {
+  const float e = __expf(-x);
+  return e > 1e30f ? 0.0f : __fdividef(1.0f, 1.0f + e);
+}
+
+// (clip, tile within the clip) of a CTA's tile sequence blockIdx.x, + gridDim.x, ...
+struct TileWalk {
+  int b, tic;
+  __device__ TileWalk(unsigned first, int tpc) : b((int)(first / (unsigned)tpc)), tic((int)(first % (unsigned)tpc)) {}
+  __device__ void step(unsigned n, int tpc) {
+    tic += (int)n;
+    while (tic >= tpc) { tic -= tpc; ++b; }
+  }
+};
+
+}  // namespace
+
+// KT > 0: Cin = 1, d = 1 and k = KT known at compile time (shuffle builder); KT = 0: any Cin * k <= KP, any d
+template <int ARCH, int KP, int KT>
+__global__ void __launch_bounds__(TP_THREADS, 1)
+toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
+  constexpr int W = ARCH == 1 ? 64 : 32;       // conv output channels
+  constexpr int N = W + 32;                    // + residual rows
+  constexpr int HC = KP / 8;                   // 16-byte chunks of the hi (and of the lo) part of a row
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* atile = smem;                                          // TP_STAGES x 16 KB
+  uint8_t* wsm = atile + (size_t)TP_STAGES * 16384;               // N rows x 128 B (12 KB reserved)
+  uint8_t* estage = wsm + 12288;                                  // per epilogue warp 4 KB
+  float* aff = reinterpret_cast<float*>(estage + (size_t)TP_EPI_WARPS * 4096);   // [2][W] scale * inv_sw, shift of one clip; per set
+  int* ktab = reinterpret_cast<int*>(aff + TP_ESETS * 2 * 64);    // [KP][2] = {channel offset (floats), look-back (samples)}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ktab + 2 * 32);
+  uint64_t* a_full = bars;                  // [TP_STAGES]  builders -> MMA
+  uint64_t* a_empty = a_full + TP_STAGES;   // [TP_STAGES]  MMA -> builders
+  uint64_t* t_full = a_empty + TP_STAGES;   // [TP_SLOTS]   MMA -> epilogue
+  uint64_t* t_empty = t_full + TP_SLOTS;    // [TP_SLOTS]   epilogue -> MMA
+  uint64_t* wfull = t_empty + TP_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int MMA_WARP = 0;   // lane 0 of builder warp 0 doubles as the MMA issuer
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TP_STAGES; ++i) { mbar_init(&a_full[i], TP_BUILD_WARPS); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < TP_SLOTS; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    mbar_init(wfull, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < KP) {
+    const int kap = threadIdx.x;
+    const int ci = kap / a.k, j = kap - ci * a.k;
+    const bool used = kap < a.Cin * a.k;
+    ktab[2 * kap] = used ? ci : -1;
+    ktab[2 * kap + 1] = used ? (a.k - 1 - j) * a.d : 0;
+  }
+  if (warp == MMA_WARP) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // the next kernel (block 1) may be scheduled as our CTAs retire; it waits for our completion itself
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const int tpc = (int)((a.T + 127) / 128);     // tiles per clip
+
+  if (warp < TP_BUILD_WARPS) {
+    // ================================ Toeplitz tile builders (thread = row) ================================
+    const int r = threadIdx.x;
+    // thread 0 also issues the tile's MMAs once all four builder warps have arrived (rotating this duty over the
+    // builder warps was measured slower: every warp then stalls on the slowest one)
+    const bool issuer = threadIdx.x == 0;
+    constexpr uint32_t idesc = make_idesc(FMT_F16, FMT_F16, 128, N);
+    const uint32_t a_lo0 = ((smem_u32(atile) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t w_lo = ((smem_u32(wsm) & 0x3FFFFu) >> 4) | (1u << 16);
+    if (issuer) {
+      mbar_arrive_expect_tx(wfull, (uint32_t)(N * 128));
+      for (int p = 0; p < N / 32; ++p) tma_load_3d(wsm + (size_t)p * 4096, &w_map, wfull, 0, p * 32, 0);
+    }
+    const long long hist = (long long)(a.k - 1) * a.d;
+    constexpr bool fast = KT > 0;
+    int st = 0;
+    uint32_t empty_phase = ~0u, full_phase = 0, tempty_phase = ~0u;
+    // (clip, tile in clip) of the current tile and of the prefetched one advance incrementally: no 64-bit divisions
+    TileWalk cur(blockIdx.x, tpc), pre(blockIdx.x, tpc);
+    for (int i = 0; i < TP_PREFETCH; ++i) pre.step(gridDim.x, tpc);
+    int slot = 0;
+    bool first = true;
+    // fast path: the two x values of a thread are loaded two tiles ahead (registers), so that the DRAM round trip
+    // of the one-pass input never sits in the per-tile dependency chain
+    auto load_x = [&](const TileWalk& w, float& xcur, float& xprev) {
+      xcur = 0.f; xprev = 0.f;
+      if (w.b < a.B) {
+        const long long tt = (long long)w.tic * 128 + r, row = a.in_row0 + tt;
+        const float* xp = a.x + (long long)w.b * a.in_clip_stride;
+        if (tt < a.T) xcur = __ldg(xp + row);
+        if (row >= 32 && tt - 32 < a.T) xprev = __ldg(xp + row - 32);
+      }
+    };
+    float xc_a = 0.f, xp_a = 0.f, xc_b = 0.f, xp_b = 0.f;
+    TileWalk nx(blockIdx.x, tpc);
+    if (fast) {
+      load_x(nx, xc_a, xp_a);
+      nx.step(gridDim.x, tpc);
+      load_x(nx, xc_b, xp_b);
+      nx.step(gridDim.x, tpc);
+    }
+    for (; cur.b < a.B; cur.step(gridDim.x, tpc), pre.step(gridDim.x, tpc)) {
+      const int b = cur.b;
+      const long long t = (long long)cur.tic * 128 + r;
+      const float* xc = a.x + (long long)b * a.in_clip_stride;
+      {
+        // x is read once, straight from HBM: pull the window this warp will need a few tiles from now towards
+        // the SM (each lane one 128-byte line per input channel), otherwise every tile pays a DRAM round trip
+        if (!fast && pre.b < a.B) {
+          const int pb = pre.b;
+          const long long p0 = a.in_row0 + (long long)pre.tic * 128 + 32 * warp - hist;   // first sample needed
+          const long long idx = p0 + 32LL * lane;
+          if (idx < p0 + hist + 32 + 31 && idx >= 0 && idx < a.in_rows) {
+            const float* pp = a.x + (long long)pb * a.in_clip_stride + idx;
+            for (int ci = 0; ci < a.Cin; ++ci)
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(pp + (long long)ci * a.in_rows));
+          }
+        }
+      }
+      uint32_t hi[KP / 2], lo[KP / 2];
+      if (KT > 0) {
+        // Cin = 1, d = 1: every lane loads and splits only its own sample (and the one 32 rows earlier); the other
+        // k - 1 columns of its Toeplitz row are its neighbours' values, fetched with warp shuffles
+        float xc0 = xc_a * kActScale, xp0 = xp_a * kActScale;     // the tile holds x * kActScale, clamped to the fp16 range
+        if (fmaxf(fabsf(xc0), fabsf(xp0)) > 65504.f) {
+          *a.sat_flag = 1u;
+          xc0 = fminf(fmaxf(xc0, -65504.f), 65504.f);
+          xp0 = fminf(fmaxf(xp0, -65504.f), 65504.f);
+        }
+        xc_a = xc_b; xp_a = xp_b;
+        load_x(nx, xc_b, xp_b);              // two tiles ahead (issuing them after the proxy fence instead was measured slower)
+        nx.step(gridDim.x, tpc);
+        uint32_t ch0, cl0, ph0, pl0;
+        split16_pair(make_float2(xc0, xp0), ch0, cl0);              // ch0 = {h(cur), h(prev)}, cl0 = {l(cur), l(prev)}
+        const uint32_t curp = __byte_perm(ch0, cl0, 0x5410);        // {h(cur), l(cur)}
+        const uint32_t prevp = __byte_perm(ch0, cl0, 0x7632);       // {h(prev), l(prev)}
+        (void)ph0; (void)pl0;
+        uint32_t col[16];                                           // col[kappa] = {h, l} of x[t - (k-1-kappa)]
+#pragma unroll
+        for (int kap = 0; kap < 16; ++kap) {
+          constexpr int kt = KT > 0 ? KT : 1;
+          const int sft = kt - 1 - kap;                             // look-back of column kappa (compile time)
+          uint32_t v = 0;
+          if (sft == 0) v = curp;
+          else if (sft > 0) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, curp, sft & 31);
+            const uint32_t dn = __shfl_down_sync(0xffffffffu, prevp, (32 - sft) & 31);
+            v = lane >= sft ? up : dn;
+          }
+          col[kap] = v;
+        }
+#pragma unroll
+        for (int q2 = 0; q2 < 8; ++q2) {
+          hi[q2] = __byte_perm(col[2 * q2], col[2 * q2 + 1], 0x5410);
+          lo[q2] = __byte_perm(col[2 * q2], col[2 * q2 + 1], 0x7632);
+        }
+      } else {
+#pragma unroll
+        for (int kap = 0; kap < KP; kap += 2) {
+          float v[2];
+#pragma unroll
+          for (int qq = 0; qq < 2; ++qq) {
+            const int ci = ktab[2 * (kap + qq)], back = ktab[2 * (kap + qq) + 1];
+            const long long row = a.in_row0 + t - back;
+            v[qq] = (ci >= 0 && row >= 0 && t < a.T) ? __ldg(xc + (long long)ci * a.in_rows + row) * kActScale : 0.f;
+          }
+          if (fmaxf(fabsf(v[0]), fabsf(v[1])) > 65504.f) {
+            *a.sat_flag = 1u;
+            v[0] = fminf(fmaxf(v[0], -65504.f), 65504.f);
+            v[1] = fminf(fmaxf(v[1], -65504.f), 65504.f);
+          }
+          split16_pair(make_float2(v[0], v[1]), hi[kap >> 1], lo[kap >> 1]);
+        }
+      }
+      mbar_wait(&a_empty[st], (empty_phase >> st) & 1u);
+      empty_phase ^= 1u << st;
+      uint8_t* rowp = atile + (size_t)st * 16384 + r * 128;
+#pragma unroll
+      for (int c = 0; c < HC; ++c) {
+        *reinterpret_cast<uint4*>(rowp + ((c ^ (r & 7)) * 16)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+        *reinterpret_cast<uint4*>(rowp + (((HC + c) ^ (r & 7)) * 16)) =
+            make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+      }
+      fence_proxy_async();       // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[st]);
+      if (issuer) {
+        // ---- MMA issue for this tile ----
+        if (first) mbar_wait(wfull, 0);
+        first = false;
+        mbar_wait(&t_empty[slot], (tempty_phase >> slot) & 1u);
+        tempty_phase ^= 1u << slot;
+        mbar_wait(&a_full[st], (full_phase >> st) & 1u);
+        full_phase ^= 1u << st;
+        tc_fence_after();
+        const uint32_t a_lo = a_lo0 + (uint32_t)st * (16384 >> 4);
+        const uint32_t dcol = tmem + (uint32_t)(slot * 128);
+        uint32_t acc = 0;
+        // terms: A hi * B hi, A hi * B lo, A lo * B hi; K16 slice s sits 2*s chunks into the hi / lo part
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t ao = (term == 2) ? HC : 0, bo = (term == 1) ? HC : 0;
+#pragma unroll
+          for (int s2 = 0; s2 < KP / 16; ++s2) {
+            const uint64_t da = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (a_lo + ao + 2 * s2);
+            const uint64_t db = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (w_lo + bo + 2 * s2);
+            umma_f16(dcol, da, db, idesc, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(&a_empty[st]);
+        umma_commit(&t_full[slot]);
+      }
+      __syncwarp();
+      st = (st + 1 == TP_STAGES) ? 0 : st + 1;
+      slot = (slot + 1 == TP_SLOTS) ? 0 : slot + 1;
+    }
+  } else {
+    // ================================ epilogue (thread = TMEM lane = tile row) ================================
+    const int ew = warp - TP_BUILD_WARPS;
+    const int eset = ew >> 2, quad = ew & 3;
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+    uint8_t* stage = estage + (size_t)ew * 4096;
+    float* saff = aff + eset * 128;          // [0,64) scale * inv_sw, [64,128) shift (this set's current clip)
+    const int st_lane = quad * 32 + lane;    // index of this thread within its set
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // scale / shift come from the fold kernel just before us
+    const float oscale = a.out_fmt == FMT_SPLIT16 ? kActScale : 1.0f;
+    const float inv_sr = a.inv_sr * oscale;
+    const float2 slope2 = make_float2(a.slope, a.slope), isr2 = make_float2(inv_sr, inv_sr);
+    const bool slope_le1 = a.slope <= 1.0f;
+    int cur_b = -1;
+    // this set takes tiles q = eset, eset + ESETS, ... of the CTA's sequence
+    TileWalk cur(blockIdx.x, tpc);
+    for (int i = 0; i < eset; ++i) cur.step(gridDim.x, tpc);
+    int qi = eset;     // index of the tile in this CTA's sequence: slot qi % SLOTS, the slot's (qi / SLOTS)-th use
+    for (; cur.b < a.B; ) {
+      const int slot = qi % TP_SLOTS;
+      const int b = cur.b;
+      const long long t0 = (long long)cur.tic * 128 + quad * 32;   // first row of this warp
+      if (b != cur_b) {     // affine of this clip (the set's 4 warps share one table)
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");   // everyone is done with the old table
+        if (st_lane < W) {
+          // GCN: [tanh | sigmoid] halves sit one padded width (32) apart in scale/shift
+          // TCN: PReLU is positively homogeneous, so the output scale of a SPLIT16 plane folds into the affine
+          const float fo = ARCH == 0 ? oscale : 1.0f;
+          saff[st_lane] = __ldg(a.scale + (long long)b * a.ld_affine + st_lane) * a.inv_sw * fo;
+          saff[64 + st_lane] = __ldg(a.shift + (long long)b * a.ld_affine + st_lane) * fo;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
+        cur_b = b;
+      }
+      mbar_wait(&t_full[slot], (uint32_t)((qi / TP_SLOTS) & 1));
+      tc_fence_after();
+      const uint32_t col0 = lane_base + (uint32_t)(slot * 128);
+      uint4 ch[8];
+      bool sat = false;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {          // 16 output channels at a time
+        float o[16];
+        uint32_t u[16], v[16];
+        tp_ld16(col0 + 16 * h, u);
+        tp_ld16(col0 + W + 16 * h, v);
+        if (ARCH == 0) {
+          tmem_ld_wait();
+          if (h == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[slot]);
+          }
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            const float2 sc2 = *reinterpret_cast<const float2*>(saff + 16 * h + c);
+            const float2 sh2 = *reinterpret_cast<const float2*>(saff + 64 + 16 * h + c);
+            const float2 y = __ffma2_rn(make_float2(__uint_as_float(u[c]), __uint_as_float(u[c + 1])), sc2, sh2);
+            const float2 p = prelu2(y, slope2, slope_le1);
+            const float2 r2 = __ffma2_rn(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), isr2, p);
+            o[c] = r2.x;
+            o[c + 1] = r2.y;
+          }
+        } else {
+          uint32_t g[16];
+          tp_ld16(col0 + 32 + 16 * h, g);
+          tmem_ld_wait();
+          if (h == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[slot]);
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float yt = fmaf(__uint_as_float(u[c]), saff[16 * h + c], saff[64 + 16 * h + c]);
+            const float ys = fmaf(__uint_as_float(g[c]), saff[32 + 16 * h + c], saff[96 + 16 * h + c]);
+            o[c] = fmaf(__uint_as_float(v[c]), inv_sr, tp_tanh(yt) * tp_sigmoid(ys) * oscale);
+          }
+        }
+        if (a.out_fmt == FMT_SPLIT16) {
+          uint32_t hi[8], lo[8];
+          float vmax = 0.f;
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) vmax = fmaxf(vmax, fmaxf(fabsf(o[c]), fabsf(o[c + 1])));
+          if (vmax > 65504.f) {     // beyond the fp16 range of the SPLIT16 planes: clamp and flag (rare)
+            sat = true;
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) split16_pair_clamped(make_float2(o[c], o[c + 1]), hi[c >> 1], lo[c >> 1]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) split16_pair(make_float2(o[c], o[c + 1]), hi[c >> 1], lo[c >> 1]);
+          }
+          // row = [hi ch 0..31 (chunks 0-3) | lo ch 0..31 (chunks 4-7)]
+          ch[2 * h] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          ch[2 * h + 1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          ch[4 + 2 * h] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          ch[4 + 2 * h + 1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        } else {   // FMT_CL
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4)
+            ch[4 * h + c4] = make_uint4(__float_as_uint(o[4 * c4]), __float_as_uint(o[4 * c4 + 1]),
+                                        __float_as_uint(o[4 * c4 + 2]), __float_as_uint(o[4 * c4 + 3]));
+        }
+      }
+      if (sat && t0 + lane < a.T) *a.sat_flag = 1u;
+      long long left = a.T - t0;
+      const int nvalid = left > 32 ? 32 : (left < 0 ? 0 : (int)left);
+      uint8_t* dst = reinterpret_cast<uint8_t*>(a.out) + (long long)b * a.out_clip_stride * (a.out_fmt == FMT_SPLIT16 ? 2 : 4) +
+                     (a.out_row0 + t0) * 128LL;
+      warp_store_rows<8>(stage, ch, lane, dst, nvalid);
+      for (int i = 0; i < TP_ESETS; ++i) cur.step(gridDim.x, tpc);
+      qi += TP_ESETS;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------ host side
+
+static size_t tp_smem_bytes() {
+  return (size_t)TP_STAGES * 16384 + 12288 + (size_t)TP_EPI_WARPS * 4096 + TP_ESETS * 2 * 64 * 4 + 2 * 32 * 4 + 256 + 1024;
+}
+
+bool toep_eligible(int arch, int Cin, int C, int k, int out_fmt) {
+  (void)arch;
+  if (C != 32 || Cin < 1 || k < 1 || Cin * k > 32) return false;
+  return out_fmt == FMT_SPLIT16 || out_fmt == FMT_CL;
+}
+
+// B operand: N = W + 32 rows x 128 B; row n = [hi kappa 0..Kp-1 | lo kappa 0..Kp-1 | unused], kappa = ci*k + j.
+// Rows < W: conv weight of channel n (GCN: original order = [tanh 32 | sigmoid 32]); rows W..W+31: residual
+// 1x1 of output channel n - W, non-zero only in the zero-shift columns j = k-1.
+void toep_pack_weights(int arch, int Cin, int k, const float* conv_w /*[W][Cin][k]*/, const float* res_w /*[32][Cin]*/,
+                       std::vector<uint16_t>& out, float* inv_sw, float* inv_sr, int* Kp_out) {
+  const int W = arch == 1 ? 64 : 32, N = W + 32;
+  const int Kp = Cin * k <= 16 ? 16 : 32;
+  *Kp_out = Kp;
+  out.assign((size_t)N * 64, 0);
+  auto pow2_scale = [](const float* w, size_t n) {
+    float mx = 0.f;
+    for (size_t i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(w[i]));
+    if (!(mx > 0.f) || !isfinite(mx)) return 1.0f;
+    int e;
+    frexpf(mx, &e);
+    return ldexpf(1.0f, 10 - e);
+  };
+  const float sw = pow2_scale(conv_w, (size_t)W * Cin * k), sr = pow2_scale(res_w, (size_t)32 * Cin);
+  *inv_sw = 1.0f / sw;
+  *inv_sr = 1.0f / sr;
+  auto put = [&](int row, int kap, float v) {
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    out[(size_t)row * 64 + kap] = __half_as_ushort(h);
+    out[(size_t)row * 64 + Kp + kap] = __half_as_ushort(l);
+  };
+  for (int n = 0; n < W; ++n)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int j = 0; j < k; ++j) put(n, ci * k + j, conv_w[((size_t)n * Cin + ci) * k + j] * sw);
+  for (int n = 0; n < 32; ++n)
+    for (int ci = 0; ci < Cin; ++ci) put(W + n, ci * k + (k - 1), res_w[(size_t)n * Cin + ci] * sr);
+}
+
+cudaError_t launch_toep_block(const ToepLaunch& L, cudaStream_t s) {
+  const ToepArgs& a = L.a;
+  if (a.B <= 0 || a.T <= 0) return cudaSuccess;
+  const int W = L.arch == 1 ? 64 : 32, N = W + 32;
+  ToepMapCache local;
+  ToepMapCache* c = L.cache ? L.cache : &local;
+  CUtensorMap& w_map = *reinterpret_cast<CUtensorMap*>(c->w_map);
+  if (c->w != L.wpacked) {
+    if (!make_plane_map(&w_map, L.wpacked, 64, (uint64_t)N, 1, (uint64_t)N * 64, 32)) return cudaErrorInvalidValue;
+    c->w = L.wpacked;
+  }
+  // kernel variant: compile-time tap count for the common first-block shapes (Cin = 1, d = 1)
+  int kt = 0;
+  if (a.Cin == 1 && a.d == 1 && L.Kp == 16 && (a.k == 3 || a.k == 15)) kt = a.k;
+  void (*fn)(CUtensorMap, ToepArgs) = nullptr;
+  int fi = 0;
+#define NASR_TOEP_PICK(ARCH_, KP_, KT_, IDX_) \
+  if (L.arch == ARCH_ && L.Kp == KP_ && kt == KT_) { fn = toep_first_kernel<ARCH_, KP_, KT_>; fi = IDX_; }
+  NASR_TOEP_PICK(0, 16, 0, 0) NASR_TOEP_PICK(0, 32, 0, 1) NASR_TOEP_PICK(0, 16, 3, 2) NASR_TOEP_PICK(0, 16, 15, 3)
+  NASR_TOEP_PICK(1, 16, 0, 4) NASR_TOEP_PICK(1, 32, 0, 5) NASR_TOEP_PICK(1, 16, 3, 6) NASR_TOEP_PICK(1, 16, 15, 7)
+#undef NASR_TOEP_PICK
+  if (!fn) return cudaErrorNotSupported;
+  const size_t smem = tp_smem_bytes();
+  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
+  if (!attr_set[fi]) {
+    cudaError_t err = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    attr_set[fi] = true;
+  }
+  const long long ntiles = ((a.T + 127) / 128) * a.B;
+  long long grid = L.sm_count < ntiles ? L.sm_count : ntiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)TP_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = L.pdl ? 1 : 0;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, fn, w_map, a);
+  if (err != cudaSuccess) return err;
+  return cudaGetLastError();
+}
+
+}  // namespace nasr

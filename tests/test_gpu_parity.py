@@ -215,6 +215,22 @@ def test_fp16_range_guard_falls_back_to_fp32_kernels():
     assert m.saturated() is False and torch.isfinite(small).all() and torch.isfinite(y_dev).all()
 
 
+@pytest.mark.parametrize("cname", ["cfg2", "cfg3", "tcn-shipped"])
+@pytest.mark.parametrize("gain", [1e-5, 1e-3, 4.0])
+def test_input_level_does_not_cost_accuracy(cname, gain):
+    """The split-fp16 planes hold value * 2^6, so that quiet material (-100 dBFS here) keeps fp32-grade
+    accuracy (fp16 lo parts would otherwise go subnormal) and hot material still fits the fp16 range."""
+    cfg = O.CONFIGS[cname]
+    sd = O.config_state(cname)
+    m = build_model(cfg, sd, DEV)
+    x = O.make_input(1, 1, 30000) * gain
+    cond = torch.tensor([[0.5, 0.5]])
+    ref = O.forward(sd, O.config_dilations(cfg), x, cond)
+    y = m(x.to(DEV), cond.to(DEV))
+    assert rel_err(y, ref) <= REL_TOL
+    assert m.saturated() is False
+
+
 def test_cfg5_long_stream_chunked_equals_oneshot_and_cpu_prefix():
     """BASELINE cfg5 (streaming, 65 536-sample chunks, per-block history carried): GPU chunked ==
     GPU one-shot on a 5-minute prefix, and the first 30 s against the CPU oracle."""
