@@ -15,6 +15,7 @@
 #include "toep_block.cuh"
 #include <cuda_fp16.h>
 #include <cmath>
+#include <cstdlib>
 
 namespace nasr {
 using namespace sm100;
@@ -171,7 +172,10 @@ toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
         }
       }
       uint32_t hi[KP / 2], lo[KP / 2];
-      if (KT > 0) {
+      if (a.dbg & 2) {   // dev: no tile build
+#pragma unroll
+        for (int i = 0; i < KP / 2; ++i) hi[i] = lo[i] = 0;
+      } else if (KT > 0) {
         // Cin = 1, d = 1: every lane loads and splits only its own sample (and the one 32 rows earlier); the other
         // k - 1 columns of its Toeplitz row are its neighbours' values, fetched with warp shuffles
         float xc0 = xc_a * kActScale, xp0 = xp_a * kActScale;     // the tile holds x * kActScale, clamped to the fp16 range
@@ -305,6 +309,18 @@ toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
       mbar_wait(&t_full[slot], (uint32_t)((qi / TP_SLOTS) & 1));
       tc_fence_after();
       const uint32_t col0 = lane_base + (uint32_t)(slot * 128);
+      if (a.dbg & 1) {   // dev: drain only
+        uint32_t u[16];
+        tp_ld16(col0, u);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[slot]);
+        if (u[0] == 0x12345678u) *a.sat_flag = 2u;
+        for (int i = 0; i < TP_ESETS; ++i) cur.step(gridDim.x, tpc);
+        qi += TP_ESETS;
+        continue;
+      }
       uint4 ch[8];
       bool sat = false;
 #pragma unroll
@@ -433,7 +449,12 @@ void toep_pack_weights(int arch, int Cin, int k, const float* conv_w /*[W][Cin][
 }
 
 cudaError_t launch_toep_block(const ToepLaunch& L, cudaStream_t s) {
-  const ToepArgs& a = L.a;
+  ToepArgs a = L.a;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("NASR_TOEP_DBG"); dbg = e ? atoi(e) : 0; }
+    a.dbg = dbg;
+  }
   if (a.B <= 0 || a.T <= 0) return cudaSuccess;
   const int W = L.arch == 1 ? 64 : 32, N = W + 32;
   ToepMapCache local;

@@ -22,6 +22,7 @@ struct ToepArgs {
   int ld_affine;
   float slope, inv_sw, inv_sr;
   unsigned int* sat_flag;
+  int dbg;                     // dev only (NASR_TOEP_DBG): 1 = epilogue only drains TMEM, 2 = builders skip the tile build
 };
 
 struct ToepMapCache {
