@@ -71,7 +71,10 @@ struct FoldArgs {
   float eps;
   float* scale; float* shift;  // [B][Wp]
 };
-cudaError_t launch_fold(const FoldArgs* blocks_dev, const float* cond, int n_blocks, int B, int maxW, cudaStream_t s);
+#define NASR_COND_INLINE_MAX 64
+// cond_inline_host (optional, <= NASR_COND_INLINE_MAX floats): cond [B][cond_dim] passed by value instead of `cond`
+cudaError_t launch_fold(const FoldArgs* blocks_dev, const float* cond, int n_blocks, int B, int maxW, cudaStream_t s,
+                        const float* cond_inline_host = nullptr, int n_inline = 0);
 
 // streaming helpers
 cudaError_t launch_copy_rows(const void* src, long long src_clip_stride, long long src_row0,

@@ -7,6 +7,7 @@
 #include "ring_block.cuh"
 #include "toep_block.cuh"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -74,6 +75,7 @@ struct nasr_engine {
   int64_t launches = 0;
   int64_t sat_fallbacks = 0;
   bool pdl = true;   // NASR_PDL=0 turns programmatic dependent launch off (dev)
+  bool zero_copy = true;   // NASR_ZEROCOPY=0: always stage y through device memory on the host-tensor path
 };
 
 namespace {
@@ -332,6 +334,7 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
   e->tc_cache.resize(n);
   e->ring_cache.resize(n);
   if (const char* env = getenv("NASR_PDL")) e->pdl = atoi(env) != 0;
+  if (const char* env = getenv("NASR_ZEROCOPY")) e->zero_copy = atoi(env) != 0;
   const float* p = w;
   std::vector<FoldArgs> fold(n);
   int rc = NASR_OK;
@@ -458,10 +461,17 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
   return NASR_OK;
 }
 
+static int set_cond_impl(nasr_engine* e, const float* cond_dev, const float* cond_inline_host, int B, void* stream);
+
 int nasr_set_cond(nasr_engine* e, const float* cond_dev, int B, void* stream) {
+  return set_cond_impl(e, cond_dev, nullptr, B, stream);
+}
+
+// cond_inline_host: host copy of cond small enough to ride in the fold kernel's parameters (host-tensor path)
+static int set_cond_impl(nasr_engine* e, const float* cond_dev, const float* cond_inline_host, int B, void* stream) {
   if (!e) return NASR_ERR_INVALID;
   if (B < 1) return fail(e, NASR_ERR_INVALID, "B must be >= 1");
-  if (e->desc.has_film && e->desc.cond_dim > 0 && !cond_dev)
+  if (e->desc.has_film && e->desc.cond_dim > 0 && !cond_dev && !cond_inline_host)
     return fail(e, NASR_ERR_INVALID, "cond is NULL but cond_dim > 0");
   DeviceGuard guard(e->device);
   cudaStream_t s = (cudaStream_t)stream;
@@ -496,7 +506,7 @@ int nasr_set_cond(nasr_engine* e, const float* cond_dev, int B, void* stream) {
     NASR_CUDA(e, cudaMemcpy(e->fold_dev, fold.data(), sizeof(FoldArgs) * n, cudaMemcpyHostToDevice));
     e->fold_valid = true;
   }
-  NASR_CUDA(e, launch_fold(e->fold_dev, cond_dev, n, B, maxW, s));
+  NASR_CUDA(e, launch_fold(e->fold_dev, cond_dev, n, B, maxW, s, cond_inline_host, cond_inline_host ? B * e->desc.cond_dim : 0));
   e->launches += 1;
   e->condB = B;
   return NASR_OK;
@@ -627,24 +637,67 @@ int nasr_forward_host(nasr_engine* e, const float* x_host, const float* cond_hos
   if (T == 0) return NASR_OK;
   DeviceGuard guard(e->device);
   cudaStream_t s = (cudaStream_t)stream;
+  // dev: NASR_E2E_DBG=1 prints host-side and device-side phase times of this call to stderr
+  static int dbg = -1;
+  if (dbg < 0) { const char* env = getenv("NASR_E2E_DBG"); dbg = env ? atoi(env) : 0; }
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::micro>(b - a).count();
+  };
+  const auto h0 = now();
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (dbg) for (auto& q : ev) cudaEventCreate(&q);
   const size_t xb = (size_t)B * e->desc.in_ch * T * sizeof(float);
   const size_t yb = (size_t)B * e->desc.out_ch * T * sizeof(float);
   if (e->hx.cap < xb || e->hy.cap < yb) NASR_CUDA(e, cudaStreamSynchronize(s));
   NASR_CUDA(e, ensure(e->hx, xb));
   NASR_CUDA(e, ensure(e->hy, yb));
+  if (dbg) cudaEventRecord(ev[0], s);
   NASR_CUDA(e, cudaMemcpyAsync(e->hx.p, x_host, xb, cudaMemcpyHostToDevice, s));
   const float* cdev = nullptr;
+  const float* cinl = nullptr;
   if (cd > 0 && cond_host) {
-    NASR_CUDA(e, ensure(e->hc, (size_t)B * cd * sizeof(float)));
-    NASR_CUDA(e, cudaMemcpyAsync(e->hc.p, cond_host, (size_t)B * cd * sizeof(float), cudaMemcpyHostToDevice, s));
-    cdev = (const float*)e->hc.p;
+    if ((size_t)B * cd <= NASR_COND_INLINE_MAX) {
+      cinl = cond_host;          // rides in the fold kernel's parameters: no extra DMA
+    } else {
+      NASR_CUDA(e, ensure(e->hc, (size_t)B * cd * sizeof(float)));
+      NASR_CUDA(e, cudaMemcpyAsync(e->hc.p, cond_host, (size_t)B * cd * sizeof(float), cudaMemcpyHostToDevice, s));
+      cdev = (const float*)e->hc.p;
+    }
   }
-  int rc = nasr_set_cond(e, cdev, B, stream);
+  if (dbg) cudaEventRecord(ev[1], s);
+  const auto h1 = now();
+  int rc = set_cond_impl(e, cdev, cinl, B, stream);
   if (rc != NASR_OK) return rc;
-  rc = nasr_forward(e, (const float*)e->hx.p, (float*)e->hy.p, B, T, stream);
+  // Pinned (device-mapped) y_host: the last block stores its output rows straight into host memory, so the
+  // device-to-host transfer overlaps that kernel instead of following it.  NASR_ZEROCOPY=0 turns this off.
+  float* y_direct = nullptr;
+  if (e->zero_copy) {
+    cudaPointerAttributes pa{};
+    if (cudaPointerGetAttributes(&pa, y_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+      y_direct = (float*)pa.devicePointer;
+    else
+      cudaGetLastError();   // unregistered host memory reports an error on some drivers: not ours to keep
+  }
+  rc = nasr_forward(e, (const float*)e->hx.p, y_direct ? y_direct : (float*)e->hy.p, B, T, stream);
   if (rc != NASR_OK) return rc;
-  NASR_CUDA(e, cudaMemcpyAsync(y_host, e->hy.p, yb, cudaMemcpyDeviceToHost, s));
+  if (dbg) cudaEventRecord(ev[2], s);
+  const auto h2 = now();
+  if (!y_direct) NASR_CUDA(e, cudaMemcpyAsync(y_host, e->hy.p, yb, cudaMemcpyDeviceToHost, s));
+  if (dbg) cudaEventRecord(ev[3], s);
+  const auto h3 = now();
   NASR_CUDA(e, cudaStreamSynchronize(s));
+  const auto h4 = now();
+  if (dbg) {
+    float d01 = 0, d12 = 0, d23 = 0;
+    cudaEventElapsedTime(&d01, ev[0], ev[1]);
+    cudaEventElapsedTime(&d12, ev[1], ev[2]);
+    cudaEventElapsedTime(&d23, ev[2], ev[3]);
+    fprintf(stderr, "[nasr e2e] host us: h2d-enqueue %.1f, launches %.1f, d2h-enqueue %.1f, sync-wait %.1f, total %.1f | "
+                    "device us: h2d %.1f, forward %.1f, d2h %.1f\n",
+            us(h0, h1), us(h1, h2), us(h2, h3), us(h3, h4), us(h0, h4), d01 * 1e3, d12 * 1e3, d23 * 1e3);
+    for (auto& q : ev) cudaEventDestroy(q);
+  }
   if (*e->sat_host) {
     // an activation exceeded the fp16 range of the SPLIT16 planes: redo this call on the fp32 kernels
     e->sat_fallbacks += 1;

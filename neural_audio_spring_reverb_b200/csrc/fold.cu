@@ -13,7 +13,12 @@ namespace nasr {
 //   shift = g * ((bias[w] - bn.running_mean[w]) * inv + bn.bias[w]) + beta
 // Without FiLM (TCN with cond_dim == 0, tcn.py:63-64): scale = 1, shift = bias.
 // Computed in fp64 and rounded once.
-__global__ void fold_kernel(const FoldArgs* __restrict__ blocks, const float* __restrict__ cond) {
+// small conditioning vectors travel in the kernel parameters (no separate host-to-device copy on the host-tensor path)
+struct CondInline { float v[NASR_COND_INLINE_MAX]; };
+
+__global__ void fold_kernel(const FoldArgs* __restrict__ blocks, const float* __restrict__ cond_ptr,
+                            const __grid_constant__ CondInline ci, int use_inline) {
+  const float* cond = use_inline ? ci.v : cond_ptr;
   // the first block kernel may start its prologue now; it waits (griddepcontrol.wait) before reading scale/shift
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const FoldArgs f = blocks[blockIdx.x];
@@ -37,11 +42,15 @@ __global__ void fold_kernel(const FoldArgs* __restrict__ blocks, const float* __
   }
 }
 
-cudaError_t launch_fold(const FoldArgs* blocks_dev, const float* cond, int n_blocks, int B, int maxW, cudaStream_t s) {
+cudaError_t launch_fold(const FoldArgs* blocks_dev, const float* cond, int n_blocks, int B, int maxW, cudaStream_t s,
+                        const float* cond_inline_host, int n_inline) {
   if (n_blocks <= 0 || B <= 0) return cudaSuccess;
+  CondInline ci{};
+  const int use_inline = (cond_inline_host && n_inline > 0 && n_inline <= NASR_COND_INLINE_MAX) ? 1 : 0;
+  for (int i = 0; i < (use_inline ? n_inline : 0); ++i) ci.v[i] = cond_inline_host[i];
   int threads = 32;
   while (threads < maxW && threads < 256) threads <<= 1;
-  fold_kernel<<<dim3(n_blocks, B), threads, 0, s>>>(blocks_dev, cond);
+  fold_kernel<<<dim3(n_blocks, B), threads, 0, s>>>(blocks_dev, cond, ci, use_inline);
   return cudaGetLastError();
 }
 

@@ -179,15 +179,19 @@ class FusedNetMixin:
                     eng.forward(xc.data_ptr(), y.data_ptr(), B, T, stream)
             return y
         # host tensors: the engine copies in, runs, copies out (e2e path of make_inference)
-        xc = x.detach().contiguous().float()
+        xc = x if (x.dtype == torch.float32 and x.is_contiguous() and not x.requires_grad) \
+            else x.detach().contiguous().float()
         cptr = 0
         if cond is not None:
-            cc = cond.detach().to(device="cpu", dtype=torch.float32).contiguous()
+            cc = cond if (cond.dtype == torch.float32 and cond.is_contiguous() and cond.device.type == "cpu"
+                          and not cond.requires_grad) \
+                else cond.detach().to(device="cpu", dtype=torch.float32).contiguous()
             cptr = cc.data_ptr()
         stream = torch.cuda.current_stream(dev).cuda_stream
         if chunk:
             xd = xc.to(dev, non_blocking=True)
             return self._nasr_run(xd, cond, True).cpu()
+        # pinned result: the engine's last kernel writes it directly (zero-copy), see nasr_forward_host
         y = torch.empty((B, self.out_ch, T), dtype=torch.float32, pin_memory=True)
         eng.forward_host(xc.data_ptr(), cptr, y.data_ptr(), B, T, stream)
         return y

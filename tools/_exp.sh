@@ -1,2 +1,3 @@
-for d in 0 1 2 3; do NASR_TOEP_DBG=$d timeout 60 python tools/ring_exp.py 1 2>&1 | tail -1 | cut -c1-120; done
-for d in 0 1 2 3; do NASR_TOEP_DBG=$d timeout 60 python tools/ring_exp.py 8 2>&1 | tail -1 | cut -c1-120; done
+timeout 100 python tools/e2e_probe.py 2>&1 | tail -6
+NASR_ZEROCOPY=0 timeout 100 python tools/e2e_probe.py 2>&1 | tail -2
+timeout 250 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
