@@ -22,6 +22,9 @@
  *                             (src/nasr/wrapper.py:14-57)
  *   nasr_block_forward     <- TCNBlock.forward / GCNBlock.forward on its own
  *                             (src/nasr/networks/tcn.py:73-86, gcn.py:53-61)
+ *   nasr_postprocess       <- the post-processing of make_inference: peak normalise,
+ *                             torchaudio highpass_biquad (lfilter, clamp), peak normalise
+ *                             (src/nasr/inference.py:70-78)
  *
  * Conventions
  *   - All tensors are fp32, contiguous, reference layout: x [B, in_ch, T],
@@ -156,6 +159,20 @@ NASR_API int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev
 NASR_API int nasr_block_forward(nasr_engine* e, int block, const float* x_dev, float* y_dev,
                        int B, int64_t T, void* stream);
 
+/*
+ * Post-processing of make_inference on the device (inference.py:70-78), independent of any engine handle:
+ *   out = y / max|y|  ->  lfilter(out, a_coeffs, b_coeffs) per row (zero initial state, clamped to [-1, 1] when
+ *   clamp != 0, as torchaudio.functional.lfilter does by default)  ->  out / max|out|.
+ * y_dev, out_dev: [rows, T] fp32 on the current device (may alias); b_coeffs / a_coeffs: 3 host floats each, the
+ * values torchaudio.functional.highpass_biquad passes to lfilter (un-normalised, a_coeffs[0] != 0).
+ * workspace_dev: nasr_postprocess_workspace_bytes(rows, T) bytes of device memory. Asynchronous on `stream`.
+ * The recursion runs as a chunked scan in fp64 (the reference's sequential fp32 recursion carries ~1e-3 of
+ * rounding noise for the 20 Hz filter).
+ */
+NASR_API size_t nasr_postprocess_workspace_bytes(int rows, int64_t T);
+NASR_API int nasr_postprocess(const float* y_dev, float* out_dev, int rows, int64_t T, const float* b_coeffs,
+                     const float* a_coeffs, int clamp, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Bytes of device workspace the engine holds / would hold for (B, T). */
 NASR_API size_t nasr_workspace_bytes(const nasr_engine* e, int B, int64_t T);
 
@@ -166,6 +183,9 @@ NASR_API int64_t nasr_receptive_field(const nasr_engine* e);
 NASR_API int64_t nasr_launch_count(const nasr_engine* e);       /* kernels launched by this handle so far   */
 NASR_API int nasr_block_path(const nasr_engine* e, int block);  /* 0 = fp32 FFMA, 1 = tcgen05 tap-gather, 2 = tcgen05 accumulator-ring kernel */
 NASR_API const char* nasr_version(void);
+
+/* dev only: per-CTA timeline stamps of the last ring-kernel launch made with NASR_RB_DBG=8 (tools/ring_timeline.py) */
+NASR_API int nasr_debug_ring_stamps(unsigned long long* host, int max_ctas);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ EXPORTS = (
     "nasr_set_cond", "nasr_forward", "nasr_forward_profiled", "nasr_saturated", "nasr_forward_host", "nasr_stream_reset",
     "nasr_forward_chunk", "nasr_block_forward", "nasr_workspace_bytes",
     "nasr_receptive_field", "nasr_launch_count", "nasr_block_path", "nasr_version",
+    "nasr_postprocess", "nasr_postprocess_workspace_bytes", "nasr_debug_ring_stamps",
 )
 
 
@@ -84,6 +85,12 @@ def load_library():
     lib.nasr_block_path.argtypes = [vp, i32]
     lib.nasr_version.restype = C.c_char_p
     lib.nasr_version.argtypes = []
+    lib.nasr_postprocess_workspace_bytes.restype = C.c_size_t
+    lib.nasr_postprocess_workspace_bytes.argtypes = [i32, i64]
+    lib.nasr_postprocess.restype = i32
+    lib.nasr_postprocess.argtypes = [f32p, f32p, i32, i64, C.c_void_p, C.c_void_p, i32, vp, C.c_size_t, vp]
+    lib.nasr_debug_ring_stamps.restype = i32
+    lib.nasr_debug_ring_stamps.argtypes = [C.c_void_p, i32]
     _lib = lib
     return lib
 
@@ -184,6 +191,34 @@ class Engine:
 
     def block_path(self, block: int) -> int:
         return int(self._lib.nasr_block_path(self._h, block))
+
+
+def postprocess(y, b_coeffs, a_coeffs, clamp: bool = True):
+    """inference.py:70-78 on the device: y [rows, T] (or [rows, 1, T]) fp32 CUDA tensor -> same shape, peak-normalised,
+    filtered with lfilter(a_coeffs, b_coeffs) per row, peak-normalised again. b_coeffs / a_coeffs: 3 floats each."""
+    import numpy as np
+    import torch
+
+    lib = load_library()
+    if not y.is_cuda:
+        raise RuntimeError("nasr_postprocess runs on the device only (no CPU path)")
+    shape = y.shape
+    yc = y.detach().reshape(-1, shape[-1]).contiguous().float()
+    rows, T = yc.shape
+    out = torch.empty_like(yc)
+    if rows == 0 or T == 0:
+        return out.reshape(shape)
+    ws_bytes = int(lib.nasr_postprocess_workspace_bytes(rows, T))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=y.device)
+    b = np.ascontiguousarray(np.asarray(b_coeffs, dtype=np.float32).reshape(3))
+    a = np.ascontiguousarray(np.asarray(a_coeffs, dtype=np.float32).reshape(3))
+    with torch.cuda.device(y.device):
+        stream = torch.cuda.current_stream(y.device).cuda_stream
+        rc = lib.nasr_postprocess(yc.data_ptr(), out.data_ptr(), rows, T, b.ctypes.data, a.ctypes.data, int(clamp),
+                                  ws.data_ptr(), ws_bytes, stream or None)
+    if rc != NASR_OK:
+        raise (ValueError if rc == NASR_ERR_INVALID else RuntimeError)(f"nasr_postprocess failed (nasr_status {rc})")
+    return out.reshape(shape)
 
 
 def version() -> str:

@@ -76,6 +76,11 @@ struct FoldArgs {
 cudaError_t launch_fold(const FoldArgs* blocks_dev, const float* cond, int n_blocks, int B, int maxW, cudaStream_t s,
                         const float* cond_inline_host = nullptr, int n_inline = 0);
 
+// out_net on a channels-last fp32 plane (when the last block's kernel cannot fuse it)
+cudaError_t launch_out_net(const float* plane, long long plane_clip_stride, long long row0, int Cp, int C, const float* wout,
+                           int out_ch, int final_tanh, float* y, long long y_clip_stride, long long y_rows, long long y_row0,
+                           int B, long long T, int sm_count, cudaStream_t s);
+
 // streaming helpers
 cudaError_t launch_copy_rows(const void* src, long long src_clip_stride, long long src_row0,
                              void* dst, long long dst_clip_stride, long long dst_row0,

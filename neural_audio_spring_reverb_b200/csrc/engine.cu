@@ -29,6 +29,7 @@ struct DevBuf {
 struct BlockState {
   int Cin = 0, Cinp = 0, W = 0, Wp = 0, Cout = 0, Coutp = 0, k = 0, d = 0, NC = 0, path = 0;
   int in_fmt = FMT_CL, out_fmt = FMT_CL;
+  bool split_out = false;   // last block writes a CL plane, out_net (+ tanh) runs as its own kernel
   float slope = 0.f;
   long long hist = 0;  // (k-1)*d rows of input history (custom_layers.py:71-73)
   float *wconv = nullptr, *wres = nullptr;
@@ -68,6 +69,7 @@ struct nasr_engine {
   long long streamTcap = 0;
   std::vector<DevBuf> splane;
   DevBuf scratch;
+  DevBuf sfinal;   // streaming: channels-last output of the last block when out_net runs as its own kernel
   // host path
   DevBuf hx, hy, hc;
   size_t budget_bytes = (size_t)24 << 30;
@@ -201,6 +203,7 @@ BlockArgs make_args(const nasr_engine* e, int i, int B, bool tc = true) {
     a.in_fmt = (i == 0) ? FMT_NCT : FMT_CL;
     a.out_fmt = (i == n - 1) ? FMT_FINAL : FMT_CL;
   }
+  (void)n;
   return a;
 }
 
@@ -261,6 +264,12 @@ inline size_t plane_row_bytes(const nasr_engine* e) { return (size_t)e->Cp * 4; 
 // tail slack of every activation plane: the ring kernel's grouped TMA view may read (never use) rows past
 // the last clip (ring_block.cuh)
 inline size_t plane_slack_bytes() { return (size_t)RB_SLACK_ROWS * 128; }
+// ping-pong activation planes of the one-shot forward (a split out_net needs a plane for the last block too)
+inline int planes_needed(const nasr_engine* e) {
+  const int n = (int)e->blocks.size();
+  const int outs = n - 1 + (e->blocks[n - 1].split_out ? 1 : 0);   // blocks that write a plane
+  return outs >= 2 ? 2 : outs;
+}
 
 }  // namespace
 
@@ -288,7 +297,7 @@ void nasr_engine_destroy(nasr_engine* e) {
     if (e->sat_host) cudaFreeHost((void*)e->sat_host);
     release(e->plane[0]); release(e->plane[1]);
     for (auto& p : e->splane) release(p);
-    release(e->scratch); release(e->hx); release(e->hy); release(e->hc);
+    release(e->scratch); release(e->sfinal); release(e->hx); release(e->hy); release(e->hc);
   }
   delete e;
 }
@@ -354,17 +363,18 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
     b.hist = (long long)(k - 1) * b.d;
     b.NC = pick_nc(desc->arch, Cp);
     // kernel of block blk: 0 = fp32 FFMA, 1 = tcgen05 tap-gather (tc_block.cu), 2 = tcgen05 accumulator ring
-    // (ring_block.cu; the GCN ring kernel splits the channels over two CTAs and cannot fuse out_net)
+    // (ring_block.cu; the GCN ring kernel splits the channels over two CTAs and cannot fuse out_net: that block
+    // writes a channels-last fp32 plane and a small out_net kernel follows, BlockState::split_out)
     auto path_of = [&](int blk) {
       if (desc->path == NASR_PATH_FP32 || blk < 1 || blk >= n) return 0;
-      if (desc->path == NASR_PATH_AUTO && ring_eligible(desc->arch, C, C, k, desc->dilations[blk]) &&
-          !(gcn && blk == n - 1))
-        return 2;
+      if (desc->path == NASR_PATH_AUTO && ring_eligible(desc->arch, C, C, k, desc->dilations[blk])) return 2;
       return tc_eligible(desc->arch, C, C, k) ? 1 : 0;
     };
     b.path = path_of(i);
     b.in_fmt = (i == 0) ? FMT_NCT : (b.path != 0 ? FMT_SPLIT16 : FMT_CL);
     b.out_fmt = (i == n - 1) ? FMT_FINAL : (path_of(i + 1) != 0 ? FMT_SPLIT16 : FMT_CL);
+    b.split_out = gcn && i == n - 1 && b.path == 2;
+    if (b.split_out) b.out_fmt = FMT_CL;
     if (b.Wp / b.NC > 16) { rc = fail(nullptr, NASR_ERR_INVALID, "channel count too large for the generic kernel"); break; }
 
     // packed column of each conv channel in the generic kernel's weight tiles (GCN: the tanh and
@@ -530,7 +540,8 @@ static int forward_slice(nasr_engine* e, const float* x, float* y, int b0, int B
       a.in_clip_stride = (a.in_fmt == FMT_SPLIT16) ? plane_elems * 2 : plane_elems;
       a.in_rows = T; a.in_row0 = 0;
     }
-    if (i == n - 1) {
+    const bool split_out = tc && bs.split_out;
+    if (i == n - 1 && !split_out) {
       a.out = y; a.out_clip_stride = (long long)e->desc.out_ch * T; a.out_rows = T; a.out_row0 = 0;
     } else {
       a.out = e->plane[i & 1].p;
@@ -540,6 +551,12 @@ static int forward_slice(nasr_engine* e, const float* x, float* y, int b0, int B
     if (ev) cudaEventRecord(ev[i], s);
     int rc = launch_block(e, a, i, s, /*allow_tc=*/true, /*tc_chain=*/tc);
     if (rc != NASR_OK) return rc;
+    if (split_out) {
+      cudaError_t err = launch_out_net((const float*)e->plane[i & 1].p, plane_elems, 0, e->Cp, e->C, e->wout, e->desc.out_ch,
+                                       e->desc.final_tanh, y, (long long)e->desc.out_ch * T, T, 0, B, T, e->sm_count, s);
+      if (err != cudaSuccess) return fail(e, NASR_ERR_CUDA, std::string("out_net launch: ") + cudaGetErrorString(err));
+      e->launches += 1;
+    }
   }
   if (ev) cudaEventRecord(ev[n], s);
   (void)row_bytes;
@@ -583,7 +600,7 @@ static int forward_impl(nasr_engine* e, const float* x_dev, float* y_dev, int B,
   }
   const int n = (int)e->blocks.size();
   const size_t per_clip = (size_t)T * plane_row_bytes(e);
-  const int nplanes = n >= 3 ? 2 : (n == 2 ? 1 : 0);
+  const int nplanes = planes_needed(e);
   int slice = B;
   if (nplanes > 0) {
     const size_t fit = e->budget_bytes / (per_clip * nplanes);
@@ -814,7 +831,14 @@ int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev, int B, 
       a.in_rows = bs.hist + Tcap;
       a.in_clip_stride = a.in_rows * e->Cp * (bs.in_fmt == FMT_SPLIT16 ? 2 : 1);
     }
-    if (i == n - 1) {
+    if (i == n - 1 && bs.split_out) {
+      const size_t need = (size_t)B * Tc * rb + plane_slack_bytes();
+      if (e->sfinal.cap < need) {
+        NASR_CUDA(e, cudaStreamSynchronize(s));
+        NASR_CUDA(e, ensure(e->sfinal, need));
+      }
+      a.out = e->sfinal.p; a.out_rows = Tc; a.out_row0 = 0; a.out_clip_stride = Tc * e->Cp;
+    } else if (i == n - 1) {
       a.out = y_dev; a.out_clip_stride = (long long)e->desc.out_ch * Tc; a.out_rows = Tc; a.out_row0 = 0;
     } else {
       const BlockState& nx = e->blocks[i + 1];
@@ -824,6 +848,11 @@ int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev, int B, 
     }
     int rc = launch_block(e, a, i, s);
     if (rc != NASR_OK) return rc;
+    if (i == n - 1 && bs.split_out) {
+      NASR_CUDA(e, launch_out_net((const float*)e->sfinal.p, Tc * e->Cp, 0, e->Cp, e->C, e->wout, e->desc.out_ch,
+                                  e->desc.final_tanh, y_dev, (long long)e->desc.out_ch * Tc, Tc, 0, B, Tc, e->sm_count, s));
+      e->launches += 1;
+    }
   }
   // carry: rows [Tc, Tc + hist) -> [0, hist) of every plane
   for (int i = 0; i < n; ++i) {
@@ -875,7 +904,7 @@ int nasr_block_forward(nasr_engine* e, int block, const float* x_dev, float* y_d
 size_t nasr_workspace_bytes(const nasr_engine* e, int B, int64_t T) {
   if (!e || B < 1 || T < 1) return 0;
   const int n = (int)e->blocks.size();
-  const int nplanes = n >= 3 ? 2 : (n == 2 ? 1 : 0);
+  const int nplanes = planes_needed(e);
   size_t per_clip = (size_t)T * plane_row_bytes(e);
   size_t want = per_clip * (size_t)B * nplanes;
   if (want > e->budget_bytes && nplanes > 0) {
@@ -893,8 +922,8 @@ int64_t nasr_receptive_field(const nasr_engine* e) {
   return rf;
 }
 
-// dev only (not in the public header): timeline stamps of the last ring-kernel launch
-__attribute__((visibility("default"))) int nasr_debug_ring_stamps(unsigned long long* host, int max_ctas) {
+// dev only: timeline stamps of the last ring-kernel launch
+int nasr_debug_ring_stamps(unsigned long long* host, int max_ctas) {
   return ring_debug_stamps(host, max_ctas);
 }
 

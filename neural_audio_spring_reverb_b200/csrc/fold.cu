@@ -54,6 +54,57 @@ cudaError_t launch_fold(const FoldArgs* blocks_dev, const float* cond, int n_blo
   return cudaGetLastError();
 }
 
+// out_net 1x1 (C -> out_ch, no bias) [+ tanh] on a channels-last fp32 plane (tcn.py:146-148,155, gcn.py:133-135,145-146):
+// used when the last block's kernel cannot fuse it (GCN ring kernel: the 32 channels of a row live in two CTAs).
+// A warp owns 32 consecutive rows; rows are read coalesced (LPR = Cp/4 lanes per row, one float4 each), the per-row
+// dot product is reduced with shuffles and the 32 results leave as one coalesced store per output channel.
+template <int LPR>
+__global__ void out_net_kernel(const float* __restrict__ plane, long long plane_clip_stride, long long row0, int Cp,
+                               const float* __restrict__ wout, int out_ch, int final_tanh, float* __restrict__ y,
+                               long long y_clip_stride, long long y_rows, long long y_row0, long long T) {
+  constexpr int RPI = 32 / LPR;   // rows per load instruction
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int b = blockIdx.y;
+  const int my_c = lane % LPR, my_r = lane / LPR;
+  const float* pb = plane + (long long)b * plane_clip_stride + row0 * Cp;
+  for (int o = 0; o < out_ch; ++o) {
+    const float4 w = *reinterpret_cast<const float4*>(wout + (long long)o * Cp + 4 * my_c);
+    for (long long t0 = ((long long)blockIdx.x * wpb + warp) * 32; t0 < T; t0 += (long long)gridDim.x * wpb * 32) {
+      float mine = 0.f;
+#pragma unroll
+      for (int q = 0; q < 32 / RPI; ++q) {
+        const long long t = t0 + RPI * q + my_r;
+        float part = 0.f;
+        if (t < T) {
+          const float4 v = *reinterpret_cast<const float4*>(pb + t * Cp + 4 * my_c);
+          part = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, v.w * w.w)));
+        }
+#pragma unroll
+        for (int m = LPR / 2; m >= 1; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+        // row RPI*q + j is complete in lane LPR*j; lane l collects row l
+        const float got = __shfl_sync(0xffffffffu, part, LPR * (lane % RPI));
+        if (lane / RPI == q) mine = got;
+      }
+      if (t0 + lane < T)
+        y[(long long)b * y_clip_stride + (long long)o * y_rows + y_row0 + t0 + lane] = final_tanh ? tanhf(mine) : mine;
+    }
+  }
+}
+
+cudaError_t launch_out_net(const float* plane, long long plane_clip_stride, long long row0, int Cp, int C, const float* wout,
+                           int out_ch, int final_tanh, float* y, long long y_clip_stride, long long y_rows, long long y_row0,
+                           int B, long long T, int sm_count, cudaStream_t s) {
+  (void)C;
+  if (B <= 0 || T <= 0) return cudaSuccess;
+  if (Cp != 32) return cudaErrorNotSupported;   // only the 32-channel ring kernel needs it
+  long long gx = (T + 255) / 256;               // 8 warps x 32 rows per block and pass
+  const long long cap = (long long)sm_count * 8 / B + 1;
+  if (gx > cap) gx = cap;
+  out_net_kernel<8><<<dim3((unsigned)gx, B), 256, 0, s>>>(plane, plane_clip_stride, row0, Cp, wout, out_ch, final_tanh, y,
+                                                          y_clip_stride, y_rows, y_row0, T);
+  return cudaGetLastError();
+}
+
 // copy `n_bytes` contiguous bytes for each of `count` segments
 __global__ void copy_segments_kernel(const char* __restrict__ src, long long src_stride,
                                      char* __restrict__ dst, long long dst_stride,

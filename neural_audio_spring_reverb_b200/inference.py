@@ -19,7 +19,7 @@ def _read_wav(path):
         return torchaudio.load(path)
     except Exception:
         from scipy.io import wavfile
-        sr, data = wavfile.read(path)
+        sr, data = wavfile.read(path)       # 24-bit PCM (the reference's assets) arrives as int32, left-justified
         if data.dtype == np.int16:
             data = data.astype(np.float32) / 32768.0
         elif data.dtype == np.int32:
@@ -44,10 +44,27 @@ def _write_wav(path, tensor, sample_rate):
         wavfile.write(path, int(sample_rate), tensor.squeeze(0).numpy().astype(np.float32))
 
 
-def _highpass_biquad(x, sample_rate, cutoff):
-    """20 Hz high-pass of the reference post-processing (inference.py:73)."""
-    import torchaudio
-    return torchaudio.functional.highpass_biquad(x, sample_rate, cutoff)
+def highpass_coeffs(sample_rate, cutoff_freq=20.0, Q=0.707):
+    """(b, a) of torchaudio.functional.highpass_biquad, computed with the same fp32 tensor ops on the CPU
+    (torchaudio/functional/filtering.py; the reference calls it at inference.py:73)."""
+    import math
+    dtype = torch.float32
+    cutoff = torch.as_tensor(cutoff_freq, dtype=dtype)
+    q = torch.as_tensor(Q, dtype=dtype)
+    w0 = 2 * math.pi * cutoff / sample_rate
+    alpha = torch.sin(w0) / 2.0 / q
+    b0 = (1 + torch.cos(w0)) / 2
+    b = torch.stack([b0, -1 - torch.cos(w0), b0]).to(dtype).numpy()
+    a = torch.stack([1 + alpha, -2 * torch.cos(w0), 1 - alpha]).to(dtype).numpy()
+    return b, a
+
+
+def postprocess(pred: torch.Tensor, sample_rate: int, cutoff_freq: float = 20.0) -> torch.Tensor:
+    """inference.py:70-78 on the device: normalise, 20 Hz high-pass biquad (lfilter semantics, clamp),
+    flatten to [1, N], normalise - nasr_postprocess (fp64 chunked scan), result still on the GPU."""
+    from . import _native
+    b, a = highpass_coeffs(sample_rate, cutoff_freq)
+    return _native.postprocess(pred, b, a, clamp=True).reshape(1, -1)
 
 
 def make_inference(args) -> torch.Tensor:
@@ -82,10 +99,9 @@ def make_inference(args) -> torch.Tensor:
         length_in_seconds = input.size(-1) / config["sample_rate"]
         print(f"RTF: {duration / length_in_seconds:.3f}")
 
-    pred = pred / pred.abs().max()
-    pred = _highpass_biquad(pred, config["sample_rate"], 20)
-    pred = pred.reshape(-1).unsqueeze(0).cpu()
-    pred = pred / torch.max(torch.abs(pred))
+    if not pred.is_cuda:
+        pred = pred.to(args.device)       # host-tensor forward: the post-processing still runs on the device
+    pred = postprocess(pred, config["sample_rate"], 20).cpu()
 
     if isinstance(args.input, str):
         file_name = Path(args.input).stem

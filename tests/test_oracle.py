@@ -73,3 +73,25 @@ def test_c_oracle_matches_reference_golden(name):
     T = min(meta["T"], 1500)
     y = c_oracle.forward(sd, meta["dilations"], x[..., :T].contiguous(), cond)
     assert rel_err(y, y_ref[..., :T]) <= 1e-5
+
+
+def test_postprocess_oracle_pinned_to_torchaudio():
+    """oracle/post_oracle.py (fp64 recursion) against the reference's own lines run here with torchaudio
+    (inference.py:70-78).  The reference's fp32 recursion of the 20 Hz biquad carries ~5e-4 of rounding noise, which
+    bounds how tightly the two can agree; the coefficients must match bit for bit."""
+    import torchaudio
+    from oracle import post_oracle as P
+    b, a = P.highpass_coeffs(48000)
+    x = torch.zeros(1, 8)
+    x[0, 0] = 1.0
+    # impulse response of torchaudio's filter vs the restated coefficients (exact in fp32 for the first taps)
+    h = torchaudio.functional.highpass_biquad(x, 48000, 20.0)[0]
+    assert abs(float(h[0]) - float(b[0] / a[0])) < 1e-7
+    torch.manual_seed(0)
+    for rows, T, sr in ((16, 3000, 48000), (8, 20000, 48000), (4, 12000, 16000)):
+        y = torch.randn(rows, 1, T) * torch.exp(-torch.arange(T) / 6000.0) + 0.03
+        got = P.postprocess(y, sr)
+        ref = P.postprocess_reference_fp32(y, sr)
+        assert got.shape == ref.shape == (1, rows * T)
+        assert float((got - ref).abs().max()) <= 2e-3
+        assert abs(float(got.abs().max()) - 1.0) < 1e-6
