@@ -34,7 +34,7 @@
 #include <cstdlib>
 
 #ifndef RB_ESETS
-#define RB_ESETS 2        // epilogue warp sets (4 warps each); set e drains steps with index % ESETS == e
+#define RB_ESETS 2        // epilogue warp sets (3 was measured: no gain at B = 8, one input stage less) (4 warps each); set e drains steps with index % ESETS == e
 #endif
 
 namespace nasr {
@@ -128,6 +128,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
   constexpr int ESETS = RB_ESETS;
   constexpr int EPI_WARPS = 4 * ESETS, PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
   constexpr int NO = (ARCH == 1) ? 16 : 32;   // output channels per thread row
+  constexpr uint32_t NDONE = 2 * ESETS;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -138,8 +139,10 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
   uint64_t* bars = (uint64_t*)(eaff + (size_t)EPI_WARPS * 256);
   uint64_t* full = bars;                       // [RB_MAX_STAGES]
   uint64_t* empty = full + RB_MAX_STAGES;      // [RB_MAX_STAGES]
-  uint64_t* done = empty + RB_MAX_STAGES;      // [2]  step complete -> epilogue
-  uint64_t* drained = done + 2;                // [1]  epilogue has read its slots -> MMA
+  // step e completes on done[e % NDONE]; only epilogue set e % ESETS waits on it, and with NDONE = 2 * ESETS that set
+  // sees every completion of the barrier in turn (a parity wait can only tell the current phase from the previous one)
+  uint64_t* done = empty + RB_MAX_STAGES;      // [NDONE]  step complete -> epilogue
+  uint64_t* drained = done + NDONE;            // [1]  epilogue has read its slots -> MMA
   uint64_t* wfull = drained + 1;               // [1]
   uint32_t* tmem_slot = (uint32_t*)(wfull + 1);
 
@@ -149,8 +152,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
   if (threadIdx.x == 0) {
     rb_stamp(a, 0);
     for (int i = 0; i < RB_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(&done[0], 1);
-    mbar_init(&done[1], 1);
+    for (uint32_t i = 0; i < NDONE; ++i) mbar_init(&done[i], 1);
     mbar_init(drained, 4);
     mbar_init(wfull, 1);
     fence_barrier_init();
@@ -270,7 +272,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           }
           umma_commit(&empty[st]);
           if (i == 0) {
-            umma_commit(&done[e & 1u]);
+            umma_commit(&done[e % NDONE]);
             pending = true;
             ++e;
           }
@@ -316,7 +318,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             for (int c = 0; c < 6; ++c) mma(a_lo, 0, bz, NS, c, 1u);
           }
           umma_commit(&empty[st]);          // the tile may be overwritten once these MMAs have read it
-          umma_commit(&done[e & 1u]);       // y_i and its residual are complete
+          umma_commit(&done[e % NDONE]);    // y_i and its residual are complete
           pending = true;
           ++e;
           st = (st + 1 == a.stages) ? 0 : st + 1;
@@ -408,10 +410,9 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         if ((int)(e % ESETS) != eset) continue;
         const long long t0 = t_span + (long long)i * a.d;
         const int cslot = i % NS, rslot = (i + NS - 1) % NS;
-        mbar_wait(&done[e & 1u], (e >> 1) & 1u);
+        mbar_wait(&done[e % NDONE], (e / NDONE) & 1u);
         tc_fence_after();
         if (e == 0 && threadIdx.x == 0) rb_stamp(a, 7);
-        float o[NO];
         if (a.dbg & 1) {   // dev: drain only
           uint32_t u[32];
           tmem_ld_32x32(lane_base + (uint32_t)(cslot * 32), u);
@@ -427,6 +428,37 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           if (u[0] == 0x12345678u && ok) *a.sat_flag = 2u;
           continue;
         }
+        const int wsw = (NCH == 8) ? (lane & 7) : ((lane >> 1) & 3);
+        uint8_t* srow = stage + lane * (NCH * 16);
+        // stage 16 outputs (one half row of the TCN, the whole group row of the GCN): chunk indices hq.. (hi / fp32)
+        // and lq.. (lo); 16-byte chunks, XOR-swizzled
+        auto stage16 = [&](const float (&o)[16], int hq, int lq) {
+          if (a.out_fmt == FMT_SPLIT16) {
+            uint32_t hi[8], lo[8];
+            float vmax = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) vmax = fmaxf(vmax, fmaxf(fabsf(o[c]), fabsf(o[c + 1])));
+            if (vmax > 65504.f) {   // beyond the fp16 range of the SPLIT16 planes: clamp and flag (rare)
+              if (ok && t0 + off < a.T) *a.sat_flag = 1u;
+#pragma unroll
+              for (int c = 0; c < 16; c += 2) split16_pair_clamped(make_float2(o[c], o[c + 1]), hi[c >> 1], lo[c >> 1]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; c += 2) split16_pair(make_float2(o[c], o[c + 1]), hi[c >> 1], lo[c >> 1]);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              *reinterpret_cast<uint4*>(srow + (((hq + q) ^ wsw) * 16)) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+              *reinterpret_cast<uint4*>(srow + (((lq + q) ^ wsw) * 16)) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+            }
+          } else {   // FMT_CL: 16 floats = 4 chunks from hq
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(srow + (((hq + q) ^ wsw) * 16)) =
+                  make_uint4(__float_as_uint(o[4 * q]), __float_as_uint(o[4 * q + 1]), __float_as_uint(o[4 * q + 2]),
+                             __float_as_uint(o[4 * q + 3]));
+          }
+        };
         if (ARCH == 0) {
           uint32_t u[32], v[32];
           tmem_ld_32x32(lane_base + (uint32_t)(cslot * 32), u);
@@ -438,8 +470,8 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(drained);
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
+          // 4 channels: affine -> PReLU -> + residual
+          auto out4 = [&](int c, float (&o4)[4]) {
             const float4 s4 = *reinterpret_cast<const float4*>(aff + c);
             const float4 h4 = *reinterpret_cast<const float4*>(aff + 32 + c);
             const float2 y0 = __ffma2_rn(make_float2(__uint_as_float(u[c]), __uint_as_float(u[c + 1])), make_float2(s4.x, s4.y),
@@ -450,7 +482,38 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                                          prelu2(y0, slope2, slope_le1));
             const float2 r1 = __ffma2_rn(make_float2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])), isr2,
                                          prelu2(y1, slope2, slope_le1));
-            o[c] = r0.x; o[c + 1] = r0.y; o[c + 2] = r1.x; o[c + 3] = r1.y;
+            o4[0] = r0.x; o4[1] = r0.y; o4[2] = r1.x; o4[3] = r1.y;
+          };
+          if (a.out_fmt == FMT_FINAL) {   // out_net 1x1 (+ tanh), row-local; lanes = consecutive samples
+            const long long t = t0 + off;
+            const bool valid = ok && t < a.T;
+            for (int oc = 0; oc < a.out_ch; ++oc) {
+              float y = 0.f;
+#pragma unroll
+              for (int c = 0; c < 32; c += 4) {
+                float o4[4];
+                out4(c, o4);
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.wout + oc * 32 + c));
+                y = fmaf(o4[0], w4.x, fmaf(o4[1], w4.y, fmaf(o4[2], w4.z, fmaf(o4[3], w4.w, y))));
+              }
+              if (a.final_tanh) y = tanhf(y);
+              if (valid)
+                ((float*)a.out)[(long long)s.b * a.out_clip_stride + (long long)oc * a.out_rows + a.out_row0 + t] = y;
+            }
+            continue;
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float o[16];
+#pragma unroll
+            for (int c = 0; c < 16; c += 4) {
+              float o4[4];
+              out4(16 * h + c, o4);
+              o[c] = o4[0]; o[c + 1] = o4[1]; o[c + 2] = o4[2]; o[c + 3] = o4[3];
+            }
+            // SPLIT16 row = [hi ch 0..31 (chunks 0-3) | lo ch 0..31 (chunks 4-7)]; fp32 row = chunks 0-7
+            if (a.out_fmt == FMT_SPLIT16) stage16(o, 2 * h, 4 + 2 * h);
+            else stage16(o, 4 * h, 0);
           }
         } else {
           uint32_t u[32], v[16];
@@ -463,60 +526,16 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(drained);
+          if (a.out_fmt == FMT_FINAL) continue;   // not produced by the GCN groups (engine: split out_net)
+          float o[16];
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             const float yt = fmaf(__uint_as_float(u[c]), aff[c], aff[32 + c]);
             const float ys = fmaf(__uint_as_float(u[16 + c]), aff[16 + c], aff[48 + c]);
             o[c] = fmaf(__uint_as_float(v[c]), inv_sr, rb_tanh(yt) * rb_sigmoid(ys) * oscale);
           }
+          stage16(o, 0, 2);   // staged group row: [hi 16 ch (chunks 0-1) | lo 16 ch (chunks 2-3)] or 4 fp32 chunks
         }
-
-        if (a.out_fmt == FMT_FINAL) {
-          if (ARCH == 0) {   // out_net 1x1 (+ tanh), row-local (single group only); lanes = consecutive samples
-            const long long t = t0 + off;
-            const bool valid = ok && t < a.T;
-            for (int oc = 0; oc < a.out_ch; ++oc) {
-              float y = 0.f;
-#pragma unroll
-              for (int c = 0; c < NO; ++c) y = fmaf(o[c], __ldg(a.wout + oc * 32 + c), y);
-              if (a.final_tanh) y = tanhf(y);
-              if (valid)
-                ((float*)a.out)[(long long)s.b * a.out_clip_stride + (long long)oc * a.out_rows + a.out_row0 + t] = y;
-            }
-          }
-          continue;
-        }
-
-        // ---- stage the row (16-byte chunks, XOR-swizzled) ----
-        uint4 ch[NCH];
-        if (a.out_fmt == FMT_SPLIT16) {
-          uint32_t hi[NO / 2], lo[NO / 2];
-          float vmax = 0.f;
-#pragma unroll
-          for (int c = 0; c < NO; c += 2) vmax = fmaxf(vmax, fmaxf(fabsf(o[c]), fabsf(o[c + 1])));
-          if (vmax > 65504.f) {   // beyond the fp16 range of the SPLIT16 planes: clamp and flag (rare)
-            if (ok && t0 + off < a.T) *a.sat_flag = 1u;
-#pragma unroll
-            for (int c = 0; c < NO; c += 2) split16_pair_clamped(make_float2(o[c], o[c + 1]), hi[c >> 1], lo[c >> 1]);
-          } else {
-#pragma unroll
-            for (int c = 0; c < NO; c += 2) split16_pair(make_float2(o[c], o[c + 1]), hi[c >> 1], lo[c >> 1]);
-          }
-#pragma unroll
-          for (int q = 0; q < NCH / 2; ++q) {
-            ch[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-            ch[NCH / 2 + q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-          }
-        } else {   // FMT_CL: fp32 row
-#pragma unroll
-          for (int q = 0; q < NCH; ++q)
-            ch[q] = make_uint4(__float_as_uint(o[4 * q]), __float_as_uint(o[4 * q + 1]), __float_as_uint(o[4 * q + 2]),
-                               __float_as_uint(o[4 * q + 3]));
-        }
-        const int wsw = (NCH == 8) ? (lane & 7) : ((lane >> 1) & 3);
-#pragma unroll
-        for (int q = 0; q < NCH; ++q)
-          *reinterpret_cast<uint4*>(stage + lane * (NCH * 16) + ((q ^ wsw) * 16)) = ch[q];
         __syncwarp();
         // ---- coalesced stores: 8 (4) lanes per row ----
 #pragma unroll
