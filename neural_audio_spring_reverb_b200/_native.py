@@ -23,7 +23,7 @@ EXPORTS = (
     "nasr_set_cond", "nasr_forward", "nasr_forward_profiled", "nasr_saturated", "nasr_forward_host", "nasr_stream_reset",
     "nasr_forward_chunk", "nasr_block_forward", "nasr_workspace_bytes",
     "nasr_receptive_field", "nasr_launch_count", "nasr_block_path", "nasr_version",
-    "nasr_postprocess", "nasr_postprocess_workspace_bytes", "nasr_debug_ring_stamps",
+    "nasr_postprocess", "nasr_postprocess_workspace_bytes", "nasr_debug_ring_stamps", "nasr_debug_ring_plan",
 )
 
 
@@ -89,6 +89,8 @@ def load_library():
     lib.nasr_postprocess_workspace_bytes.argtypes = [i32, i64]
     lib.nasr_postprocess.restype = i32
     lib.nasr_postprocess.argtypes = [f32p, f32p, i32, i64, C.c_void_p, C.c_void_p, i32, vp, C.c_size_t, vp]
+    lib.nasr_debug_ring_plan.restype = i32
+    lib.nasr_debug_ring_plan.argtypes = [i32, i32, i32, i32, i64, i64, i32, C.c_void_p]
     lib.nasr_debug_ring_stamps.restype = i32
     lib.nasr_debug_ring_stamps.argtypes = [C.c_void_p, i32]
     _lib = lib

@@ -927,6 +927,11 @@ int nasr_debug_ring_stamps(unsigned long long* host, int max_ctas) {
   return ring_debug_stamps(host, max_ctas);
 }
 
+// dev / tests: host-side launch plan of the ring kernel (no device needed)
+int nasr_debug_ring_plan(int arch, int k, int d, int B, int64_t T, int64_t in_row0, int sm_count, int64_t* out16) {
+  return ring_debug_plan(arch, k, d, B, T, in_row0, sm_count, reinterpret_cast<long long*>(out16));
+}
+
 int64_t nasr_launch_count(const nasr_engine* e) { return e ? e->launches : 0; }
 
 int nasr_block_path(const nasr_engine* e, int block) {

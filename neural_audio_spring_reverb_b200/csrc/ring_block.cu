@@ -637,6 +637,80 @@ static bool make_group_map(CUtensorMap* map, const void* base, uint64_t rext, ui
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Host-side launch plan (no CUDA calls; unit-tested on the CPU through nasr_debug_ring_plan): walk mode, span length,
+// grid, shared-memory stages, TMEM columns.  In: a.{B, T, k, d, in_row0}; cached_n > 0 skips the span-length search.
+cudaError_t ring_plan(int arch, int sm_count, long long cached_n, RingArgs& a, long long* grid_out) {
+  const int n_grp = ring_groups(arch);
+  a.n_grp = n_grp;
+  a.NS = a.k + 1;
+  if (a.NS > RB_MAX_SLOTS) return cudaErrorInvalidConfiguration;
+  a.NW = rb_weight_blocks(a.NS);
+  a.tmem_cols = 32;
+  while (a.tmem_cols < a.NS * 32) a.tmem_cols *= 2;
+  int stages = RB_MAX_STAGES;
+  while (stages > 2 && rb_smem_bytes(a.NS, stages) > 227 * 1024) --stages;
+  a.stages = stages;
+  if (rb_smem_bytes(a.NS, stages) > 227 * 1024) return cudaErrorInvalidConfiguration;
+
+  // ---- span length: n steps per span; every span pays k - 1 warm-up steps (loads + partial MMAs) ----
+  long long steps_per_strip;   // steps a whole strip needs when it is one span
+  long long strips;
+  a.NP = 0;
+  if (a.d < 128) {
+    a.mode = 0; a.G = 128 / a.d; a.L = 1;
+    steps_per_strip = (a.T + (long long)a.G * a.d - 1) / ((long long)a.G * a.d);
+    strips = a.B;
+  } else {
+    a.mode = 1; a.G = 1; a.L = (a.d + 127) / 128;
+    a.NP = (a.T + a.d - 1) / a.d;
+    steps_per_strip = a.NP;
+    strips = (long long)a.B * a.L;
+  }
+  const long long ctas = sm_count / n_grp > 0 ? sm_count / n_grp : 1;   // span walkers per group
+  long long n_max = 512;
+  if (a.mode == 0) {
+    const long long cap = (RB_SLACK_ROWS - (long long)(a.k + 1) * a.d - a.in_row0) / a.d;   // over-read bound
+    if (cap < 1) return cudaErrorInvalidConfiguration;
+    if (n_max > cap) n_max = cap;
+  }
+  if (n_max > steps_per_strip) n_max = steps_per_strip;
+  long long best_n = n_max;
+  if (cached_n > 0 && cached_n <= n_max) {
+    best_n = cached_n;
+  } else {
+    double best_cost = 1e300;
+    const double warm = 0.5 * (a.k - 1) + 1.0;    // warm-up steps are cheaper than full ones; + fixed span overhead
+    for (long long n = n_max; n >= 1; --n) {
+      const long long sps = (steps_per_strip + n - 1) / n;
+      const long long total = sps * strips;
+      const long long waves = (total + ctas - 1) / ctas;
+      const double cost = (double)waves * ((double)n + warm);
+      if (cost < best_cost - 1e-9) { best_cost = cost; best_n = n; }
+    }
+  }
+  a.n = (int)best_n;
+  a.S = (long long)a.n * a.d;
+  a.spans_per_strip = (steps_per_strip + a.n - 1) / a.n;
+  a.total_spans = a.spans_per_strip * strips;
+  long long grid = a.total_spans < ctas ? a.total_spans : ctas;
+  *grid_out = grid * n_grp;
+  return cudaSuccess;
+}
+
+// dev / tests: the plan as plain integers {mode, G, L, n, S, NP, spans_per_strip, total_spans, grid, stages, NS, NW,
+// tmem_cols, smem_bytes, n_grp, rext(mode S), jext is per plane}; returns 0 on success
+int ring_debug_plan(int arch, int k, int d, int B, long long T, long long in_row0, int sm_count, long long* out16) {
+  RingArgs a{};
+  a.B = B; a.T = T; a.k = k; a.d = d; a.in_row0 = in_row0;
+  long long grid = 0;
+  if (B <= 0 || T <= 0 || ring_plan(arch, sm_count, 0, a, &grid) != cudaSuccess) return 1;
+  const long long v[16] = {a.mode, a.G, a.L, a.n, a.S, a.NP, a.spans_per_strip, a.total_spans, grid, a.stages, a.NS, a.NW,
+                           a.tmem_cols, (long long)rb_smem_bytes(a.NS, a.stages), a.n_grp,
+                           a.mode == 0 ? a.in_row0 + a.S + a.d : 0};
+  for (int i = 0; i < 16; ++i) out16[i] = v[i];
+  return 0;
+}
+
 static unsigned long long* g_dbg_buf = nullptr;
 // dev: copy the stamps of the last launch (NASR_RB_DBG & 8) to the host; returns number of CTAs covered
 int ring_debug_stamps(unsigned long long* host, int max_ctas) {
@@ -663,63 +737,19 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
       g_dbg_buf = buf;
     }
   }
-  const int n_grp = ring_groups(L.arch);
-  a.n_grp = n_grp;
-  a.NS = a.k + 1;
-  if (a.NS > RB_MAX_SLOTS) return cudaErrorInvalidConfiguration;
-  a.NW = rb_weight_blocks(a.NS);
-  a.tmem_cols = 32;
-  while (a.tmem_cols < a.NS * 32) a.tmem_cols *= 2;
-  int stages = RB_MAX_STAGES;
-  while (stages > 2 && rb_smem_bytes(a.NS, stages) > 227 * 1024) --stages;
-  a.stages = stages;
-  const size_t smem = rb_smem_bytes(a.NS, stages);
-  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-
-  // ---- span length: n steps per span; every span pays k - 1 warm-up steps (loads + partial MMAs) ----
-  long long steps_per_strip;   // steps a whole strip needs when it is one span
-  long long strips;
-  if (a.d < 128) {
-    a.mode = 0; a.G = 128 / a.d; a.L = 1;
-    steps_per_strip = (a.T + (long long)a.G * a.d - 1) / ((long long)a.G * a.d);
-    strips = a.B;
-  } else {
-    a.mode = 1; a.G = 1; a.L = (a.d + 127) / 128;
-    a.NP = (a.T + a.d - 1) / a.d;
-    steps_per_strip = a.NP;
-    strips = (long long)a.B * a.L;
-  }
-  const long long ctas = L.sm_count / n_grp > 0 ? L.sm_count / n_grp : 1;   // span walkers per group
-  long long n_max = 512;
-  if (a.mode == 0) {
-    const long long cap = (RB_SLACK_ROWS - (long long)(a.k + 1) * a.d - a.in_row0) / a.d;   // over-read bound
-    if (cap < 1) return cudaErrorInvalidConfiguration;
-    if (n_max > cap) n_max = cap;
-  }
-  if (n_max > steps_per_strip) n_max = steps_per_strip;
   RingMapCache local;
   RingMapCache* c = L.cache ? L.cache : &local;
-  long long best_n = n_max;
-  double best_cost = 1e300;
-  if (c->n_B == a.B && c->n_T == a.T && c->n_d == a.d && c->n_k == a.k && c->n_row0 == a.in_row0 && c->n_sm == L.sm_count) {
-    best_n = c->n;
-  } else {
-  const double warm = 0.5 * (a.k - 1) + 1.0;    // warm-up steps are cheaper than full ones; + fixed span overhead
-  for (long long n = n_max; n >= 1; --n) {
-    const long long sps = (steps_per_strip + n - 1) / n;
-    const long long total = sps * strips;
-    const long long waves = (total + ctas - 1) / ctas;
-    const double cost = (double)waves * ((double)n + warm);
-    if (cost < best_cost - 1e-9) { best_cost = cost; best_n = n; }
+  const int n_grp = ring_groups(L.arch);
+  long long grid = 0;
+  {
+    long long cached_n = 0;
+    if (c->n_B == a.B && c->n_T == a.T && c->n_d == a.d && c->n_k == a.k && c->n_row0 == a.in_row0 && c->n_sm == L.sm_count)
+      cached_n = c->n;
+    cudaError_t perr = ring_plan(L.arch, L.sm_count, cached_n, a, &grid);
+    if (perr != cudaSuccess) return perr;
+    c->n_B = a.B; c->n_T = a.T; c->n_d = a.d; c->n_k = a.k; c->n_row0 = a.in_row0; c->n_sm = L.sm_count; c->n = a.n;
   }
-    c->n_B = a.B; c->n_T = a.T; c->n_d = a.d; c->n_k = a.k; c->n_row0 = a.in_row0; c->n_sm = L.sm_count; c->n = best_n;
-  }
-  a.n = (int)best_n;
-  a.S = (long long)a.n * a.d;
-  a.spans_per_strip = (steps_per_strip + a.n - 1) / a.n;
-  a.total_spans = a.spans_per_strip * strips;
-  long long grid = a.total_spans < ctas ? a.total_spans : ctas;
-  grid *= n_grp;
+  const size_t smem = rb_smem_bytes(a.NS, a.stages);
 
   static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
   CUtensorMap& in_map = *reinterpret_cast<CUtensorMap*>(c->in_map);

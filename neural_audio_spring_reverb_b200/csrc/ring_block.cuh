@@ -76,5 +76,7 @@ void ring_pack_weights(int arch, int grp, int k, const float* conv_w, const floa
                        float* inv_sw, float* inv_sr);
 cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s);
 int ring_debug_stamps(unsigned long long* host, int max_ctas);
+cudaError_t ring_plan(int arch, int sm_count, long long cached_n, RingArgs& a, long long* grid_out);
+int ring_debug_plan(int arch, int k, int d, int B, long long T, long long in_row0, int sm_count, long long* out16);
 
 }  // namespace nasr
