@@ -186,6 +186,7 @@ NASR_API const char* nasr_version(void);
 
 /* dev only: per-CTA timeline stamps of the last ring-kernel launch made with NASR_RB_DBG=8 (tools/ring_timeline.py) */
 NASR_API int nasr_debug_ring_stamps(unsigned long long* host, int max_ctas);
+NASR_API int nasr_debug_toep_stamps(unsigned long long* host, int n);   /* NASR_TOEP_DBG=8, tools/toep_timeline.py */
 /* dev / tests: host-side launch plan of the accumulator-ring kernel (no device needed); out16 = {mode, G, L, n, S, NP,
  * spans_per_strip, total_spans, grid, stages, NS, NW, tmem_cols, smem_bytes, n_grp, rext}; 0 on success */
 NASR_API int nasr_debug_ring_plan(int arch, int k, int d, int B, int64_t T, int64_t in_row0, int sm_count, int64_t* out16);

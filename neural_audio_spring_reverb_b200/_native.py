@@ -23,7 +23,7 @@ EXPORTS = (
     "nasr_set_cond", "nasr_forward", "nasr_forward_profiled", "nasr_saturated", "nasr_forward_host", "nasr_stream_reset",
     "nasr_forward_chunk", "nasr_block_forward", "nasr_workspace_bytes",
     "nasr_receptive_field", "nasr_launch_count", "nasr_block_path", "nasr_version",
-    "nasr_postprocess", "nasr_postprocess_workspace_bytes", "nasr_debug_ring_stamps", "nasr_debug_ring_plan",
+    "nasr_postprocess", "nasr_postprocess_workspace_bytes", "nasr_debug_ring_stamps", "nasr_debug_ring_plan", "nasr_debug_toep_stamps",
 )
 
 

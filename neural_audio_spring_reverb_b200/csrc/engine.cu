@@ -927,6 +927,8 @@ int nasr_debug_ring_stamps(unsigned long long* host, int max_ctas) {
   return ring_debug_stamps(host, max_ctas);
 }
 
+int nasr_debug_toep_stamps(unsigned long long* host, int n) { return toep_debug_stamps(host, n); }
+
 // dev / tests: host-side launch plan of the ring kernel (no device needed)
 int nasr_debug_ring_plan(int arch, int k, int d, int B, int64_t T, int64_t in_row0, int sm_count, int64_t* out16) {
   return ring_debug_plan(arch, k, d, B, T, in_row0, sm_count, reinterpret_cast<long long*>(out16));

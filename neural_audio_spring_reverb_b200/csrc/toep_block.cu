@@ -24,11 +24,14 @@ namespace {
 
 constexpr int TP_STAGES = 4;          // A tiles in flight
 constexpr int TP_SLOTS = 4;           // TMEM accumulator slots of 128 columns
-constexpr int TP_ESETS = 3;           // epilogue warp sets (4 warps each)
-constexpr int TP_BUILD_WARPS = 4;
+// 16 warps per CTA, split per architecture between builder groups (4 warps = 128 rows; group g builds the CTA's tiles
+// g, g + BG, ...) and epilogue sets (4 warps; set e drains tiles e, e + ES, ...): the TCN is builder-bound (2 + 2), the GCN's
+// gate math makes it epilogue-bound (1 + 3) - both measured
+template <int ARCH> struct TpCfg { static constexpr int BG = ARCH == 0 ? 2 : 1, ES = ARCH == 0 ? 2 : 3; };
+constexpr int TP_ESETS_MAX = 3;
 constexpr int TP_PREFETCH = 4;        // tiles (of this CTA) the x prefetch runs ahead
-constexpr int TP_EPI_WARPS = 4 * TP_ESETS;
-constexpr int TP_THREADS = (TP_BUILD_WARPS + TP_EPI_WARPS) * 32;   // 16 warps: 128 registers each
+constexpr int TP_EPI_WARPS = 4 * TP_ESETS_MAX;   // shared-memory sizing
+constexpr int TP_THREADS = 16 * 32;              // 16 warps: 128 registers each
 
 __device__ __forceinline__ void tp_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -46,6 +49,15 @@ __device__ __forceinline__ float tp_tanh(float x) {
 __device__ __forceinline__ float tp_sigmoid(float x) {
   const float e = __expf(-x);
   return e > 1e30f ? 0.0f : __fdividef(1.0f, 1.0f + e);
+}
+
+// dev: %globaltimer stamp (CTA 0 only): buf[tile_index * 8 + what]
+__device__ __forceinline__ void tp_stamp(const ToepArgs& a, int q, int what) {
+  if (a.dbg_buf && blockIdx.x == 0 && q < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.dbg_buf[q * 8 + what] = t;
+  }
 }
 
 // (clip, tile within the clip) of a CTA's tile sequence blockIdx.x, + gridDim.x, ...
@@ -67,6 +79,8 @@ toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
   constexpr int W = ARCH == 1 ? 64 : 32;       // conv output channels
   constexpr int N = W + 32;                    // + residual rows
   constexpr int HC = KP / 8;                   // 16-byte chunks of the hi (and of the lo) part of a row
+  constexpr int TP_BGROUPS = TpCfg<ARCH>::BG, TP_ESETS = TpCfg<ARCH>::ES, TP_BUILD_WARPS = 4 * TP_BGROUPS;
+  static_assert(TP_BUILD_WARPS + 4 * TP_ESETS == 16, "16 warps");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -74,7 +88,7 @@ toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
   uint8_t* wsm = atile + (size_t)TP_STAGES * 16384;               // N rows x 128 B (12 KB reserved)
   uint8_t* estage = wsm + 12288;                                  // per epilogue warp 4 KB
   float* aff = reinterpret_cast<float*>(estage + (size_t)TP_EPI_WARPS * 4096);   // [2][W] scale * inv_sw, shift of one clip; per set
-  int* ktab = reinterpret_cast<int*>(aff + TP_ESETS * 2 * 64);    // [KP][2] = {channel offset (floats), look-back (samples)}
+  int* ktab = reinterpret_cast<int*>(aff + TP_ESETS_MAX * 2 * 64);    // [KP][2] = {channel offset (floats), look-back (samples)}
   uint64_t* bars = reinterpret_cast<uint64_t*>(ktab + 2 * 32);
   uint64_t* a_full = bars;                  // [TP_STAGES]  builders -> MMA
   uint64_t* a_empty = a_full + TP_STAGES;   // [TP_STAGES]  MMA -> builders
@@ -87,7 +101,7 @@ toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
   constexpr int MMA_WARP = 0;   // lane 0 of builder warp 0 doubles as the MMA issuer
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TP_STAGES; ++i) { mbar_init(&a_full[i], TP_BUILD_WARPS); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < TP_STAGES; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < TP_SLOTS; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
     mbar_init(wfull, 1);
     fence_barrier_init();
@@ -114,25 +128,30 @@ toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
 
   if (warp < TP_BUILD_WARPS) {
     // ================================ Toeplitz tile builders (thread = row) ================================
-    const int r = threadIdx.x;
-    // thread 0 also issues the tile's MMAs once all four builder warps have arrived (rotating this duty over the
-    // builder warps was measured slower: every warp then stalls on the slowest one)
-    const bool issuer = threadIdx.x == 0;
+    // one builder thread is latency-bound (~1 us per tile on the timeline): two groups build alternate tiles, each with
+    // its own stages / TMEM slots (tile q -> stage q % 4, slot q % 4) and its own MMA-issuing thread
+    const int bg = warp >> 2;                  // builder group
+    const int r = threadIdx.x & 127;
+    const unsigned bstep = TP_BGROUPS * gridDim.x;
+    const unsigned bfirst = blockIdx.x + bg * gridDim.x;
+    // the group's first thread also issues its tiles' MMAs (rotating this duty over the builder warps was measured
+    // slower: every warp then stalls on the slowest one)
+    const bool issuer = r == 0;
     constexpr uint32_t idesc = make_idesc(FMT_F16, FMT_F16, 128, N);
     const uint32_t a_lo0 = ((smem_u32(atile) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t w_lo = ((smem_u32(wsm) & 0x3FFFFu) >> 4) | (1u << 16);
-    if (issuer) {
+    if (threadIdx.x == 0) {
       mbar_arrive_expect_tx(wfull, (uint32_t)(N * 128));
       for (int p = 0; p < N / 32; ++p) tma_load_3d(wsm + (size_t)p * 4096, &w_map, wfull, 0, p * 32, 0);
     }
     const long long hist = (long long)(a.k - 1) * a.d;
     constexpr bool fast = KT > 0;
-    int st = 0;
+    int st = bg;
     uint32_t empty_phase = ~0u, full_phase = 0, tempty_phase = ~0u;
     // (clip, tile in clip) of the current tile and of the prefetched one advance incrementally: no 64-bit divisions
-    TileWalk cur(blockIdx.x, tpc), pre(blockIdx.x, tpc);
-    for (int i = 0; i < TP_PREFETCH; ++i) pre.step(gridDim.x, tpc);
-    int slot = 0;
+    TileWalk cur(bfirst, tpc), pre(bfirst, tpc);
+    for (int i = 0; i < TP_PREFETCH; ++i) pre.step(bstep, tpc);
+    int slot = bg, qb = bg;
     bool first = true;
     // fast path: the two x values of a thread are loaded two tiles ahead (registers), so that the DRAM round trip
     // of the one-pass input never sits in the per-tile dependency chain
@@ -146,14 +165,44 @@ toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
       }
     };
     float xc_a = 0.f, xp_a = 0.f, xc_b = 0.f, xp_b = 0.f;
-    TileWalk nx(blockIdx.x, tpc);
+    TileWalk nx(bfirst, tpc);
     if (fast) {
       load_x(nx, xc_a, xp_a);
-      nx.step(gridDim.x, tpc);
+      nx.step(bstep, tpc);
       load_x(nx, xc_b, xp_b);
-      nx.step(gridDim.x, tpc);
+      nx.step(bstep, tpc);
     }
-    for (; cur.b < a.B; cur.step(gridDim.x, tpc), pre.step(gridDim.x, tpc)) {
+    auto issue_mma = [&](int ist, int islot, int iq) {
+      if (first) mbar_wait(wfull, 0);
+      first = false;
+      mbar_wait(&t_empty[islot], (tempty_phase >> islot) & 1u);
+      tempty_phase ^= 1u << islot;
+      mbar_wait(&a_full[ist], (full_phase >> ist) & 1u);
+      full_phase ^= 1u << ist;
+      tc_fence_after();
+      tp_stamp(a, iq, 3);                            // slot free and all builder warps arrived
+      const uint32_t a_lo = a_lo0 + (uint32_t)ist * (16384 >> 4);
+      const uint32_t dcol = tmem + (uint32_t)(islot * 128);
+      uint32_t acc = 0;
+      // terms: A hi * B hi, A hi * B lo, A lo * B hi; K16 slice s sits 2*s chunks into the hi / lo part
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t ao = (term == 2) ? HC : 0, bo = (term == 1) ? HC : 0;
+#pragma unroll
+        for (int s2 = 0; s2 < KP / 16; ++s2) {
+          const uint64_t da = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (a_lo + ao + 2 * s2);
+          const uint64_t db = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (w_lo + bo + 2 * s2);
+          umma_f16(dcol, da, db, idesc, acc);
+          acc = 1;
+        }
+      }
+      umma_commit(&a_empty[ist]);
+      umma_commit(&t_full[islot]);
+      tp_stamp(a, iq, 4);                            // MMAs issued
+    };
+    bool pend = false;
+    int pst = 0, pslot = 0;
+    for (; cur.b < a.B; cur.step(bstep, tpc), pre.step(bstep, tpc)) {
       const int b = cur.b;
       const long long t = (long long)cur.tic * 128 + r;
       const float* xc = a.x + (long long)b * a.in_clip_stride;
@@ -186,7 +235,7 @@ toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
         }
         xc_a = xc_b; xp_a = xp_b;
         load_x(nx, xc_b, xp_b);              // two tiles ahead (issuing them after the proxy fence instead was measured slower)
-        nx.step(gridDim.x, tpc);
+        nx.step(bstep, tpc);
         uint32_t ch0, cl0, ph0, pl0;
         split16_pair(make_float2(xc0, xp0), ch0, cl0);              // ch0 = {h(cur), h(prev)}, cl0 = {l(cur), l(prev)}
         const uint32_t curp = __byte_perm(ch0, cl0, 0x5410);        // {h(cur), l(cur)}
@@ -229,8 +278,10 @@ toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
           split16_pair(make_float2(v[0], v[1]), hi[kap >> 1], lo[kap >> 1]);
         }
       }
+      if (r == 0) tp_stamp(a, qb, 0);      // tile built in registers
       mbar_wait(&a_empty[st], (empty_phase >> st) & 1u);
       empty_phase ^= 1u << st;
+      if (r == 0) tp_stamp(a, qb, 1);      // stage free
       uint8_t* rowp = atile + (size_t)st * 16384 + r * 128;
 #pragma unroll
       for (int c = 0; c < HC; ++c) {
@@ -241,37 +292,20 @@ toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
       fence_proxy_async();       // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[st]);
+      if (r == 0) tp_stamp(a, qb, 2);      // arrived
       if (issuer) {
-        // ---- MMA issue for this tile ----
-        if (first) mbar_wait(wfull, 0);
-        first = false;
-        mbar_wait(&t_empty[slot], (tempty_phase >> slot) & 1u);
-        tempty_phase ^= 1u << slot;
-        mbar_wait(&a_full[st], (full_phase >> st) & 1u);
-        full_phase ^= 1u << st;
-        tc_fence_after();
-        const uint32_t a_lo = a_lo0 + (uint32_t)st * (16384 >> 4);
-        const uint32_t dcol = tmem + (uint32_t)(slot * 128);
-        uint32_t acc = 0;
-        // terms: A hi * B hi, A hi * B lo, A lo * B hi; K16 slice s sits 2*s chunks into the hi / lo part
-#pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          const uint32_t ao = (term == 2) ? HC : 0, bo = (term == 1) ? HC : 0;
-#pragma unroll
-          for (int s2 = 0; s2 < KP / 16; ++s2) {
-            const uint64_t da = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (a_lo + ao + 2 * s2);
-            const uint64_t db = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (w_lo + bo + 2 * s2);
-            umma_f16(dcol, da, db, idesc, acc);
-            acc = 1;
-          }
-        }
-        umma_commit(&a_empty[st]);
-        umma_commit(&t_full[slot]);
+        // MMA issue is deferred by one tile: by now the other builder warps have long arrived for the previous
+        // tile, so this thread never waits for them (waiting here cost 0.3 us per tile on the timeline)
+        if (pend) issue_mma(pst, pslot, qb - TP_BGROUPS);
+        pend = true; pst = st; pslot = slot;
       }
       __syncwarp();
-      st = (st + 1 == TP_STAGES) ? 0 : st + 1;
-      slot = (slot + 1 == TP_SLOTS) ? 0 : slot + 1;
+      qb += TP_BGROUPS;
+      st = (st + TP_BGROUPS) % TP_STAGES;
+      slot = (slot + TP_BGROUPS) % TP_SLOTS;
     }
+    if (issuer && pend) issue_mma(pst, pslot, qb - TP_BGROUPS);
+    __syncwarp();
   } else {
     // ================================ epilogue (thread = TMEM lane = tile row) ================================
     const int ew = warp - TP_BUILD_WARPS;
@@ -308,6 +342,7 @@ toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
       }
       mbar_wait(&t_full[slot], (uint32_t)((qi / TP_SLOTS) & 1));
       tc_fence_after();
+      if (quad == 0 && lane == 0) tp_stamp(a, qi, 5);  // accumulators seen complete
       const uint32_t col0 = lane_base + (uint32_t)(slot * 128);
       if (a.dbg & 1) {   // dev: drain only
         uint32_t u[16];
@@ -393,6 +428,7 @@ toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
       uint8_t* dst = reinterpret_cast<uint8_t*>(a.out) + (long long)b * a.out_clip_stride * (a.out_fmt == FMT_SPLIT16 ? 2 : 4) +
                      (a.out_row0 + t0) * 128LL;
       warp_store_rows<8>(stage, ch, lane, dst, nvalid);
+      if (quad == 0 && lane == 0) tp_stamp(a, qi, 6);  // rows stored
       for (int i = 0; i < TP_ESETS; ++i) cur.step(gridDim.x, tpc);
       qi += TP_ESETS;
     }
@@ -406,7 +442,7 @@ toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
 // ------------------------------------------------------------------------------------ host side
 
 static size_t tp_smem_bytes() {
-  return (size_t)TP_STAGES * 16384 + 12288 + (size_t)TP_EPI_WARPS * 4096 + TP_ESETS * 2 * 64 * 4 + 2 * 32 * 4 + 256 + 1024;
+  return (size_t)TP_STAGES * 16384 + 12288 + (size_t)TP_EPI_WARPS * 4096 + TP_ESETS_MAX * 2 * 64 * 4 + 2 * 32 * 4 + 256 + 1024;
 }
 
 bool toep_eligible(int arch, int Cin, int C, int k, int out_fmt) {
@@ -448,12 +484,27 @@ void toep_pack_weights(int arch, int Cin, int k, const float* conv_w /*[W][Cin][
     for (int ci = 0; ci < Cin; ++ci) put(W + n, ci * k + (k - 1), res_w[(size_t)n * Cin + ci] * sr);
 }
 
+static unsigned long long* g_tp_dbg = nullptr;
+int toep_debug_stamps(unsigned long long* host, int n) {
+  if (!g_tp_dbg) return 0;
+  cudaDeviceSynchronize();
+  if (n > 64 * 8) n = 64 * 8;
+  cudaMemcpy(host, g_tp_dbg, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return n;
+}
+
 cudaError_t launch_toep_block(const ToepLaunch& L, cudaStream_t s) {
   ToepArgs a = L.a;
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("NASR_TOEP_DBG"); dbg = e ? atoi(e) : 0; }
     a.dbg = dbg;
+    a.dbg_buf = nullptr;
+    if (dbg & 8) {
+      if (!g_tp_dbg) cudaMalloc(&g_tp_dbg, 64 * 8 * sizeof(unsigned long long));
+      cudaMemsetAsync(g_tp_dbg, 0, 64 * 8 * sizeof(unsigned long long), s);
+      a.dbg_buf = g_tp_dbg;
+    }
   }
   if (a.B <= 0 || a.T <= 0) return cudaSuccess;
   const int W = L.arch == 1 ? 64 : 32, N = W + 32;

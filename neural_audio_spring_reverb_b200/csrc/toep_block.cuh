@@ -22,6 +22,7 @@ struct ToepArgs {
   int ld_affine;
   float slope, inv_sw, inv_sr;
   unsigned int* sat_flag;
+  unsigned long long* dbg_buf; // dev only: per-tile timeline stamps of CTA 0
   int dbg;                     // dev only (NASR_TOEP_DBG): 1 = epilogue only drains TMEM, 2 = builders skip the tile build
 };
 
@@ -42,5 +43,6 @@ bool toep_eligible(int arch, int Cin, int C, int k, int out_fmt);
 void toep_pack_weights(int arch, int Cin, int k, const float* conv_w, const float* res_w, std::vector<uint16_t>& out,
                        float* inv_sw, float* inv_sr, int* Kp_out);
 cudaError_t launch_toep_block(const ToepLaunch& L, cudaStream_t s);
+int toep_debug_stamps(unsigned long long* host, int n);
 
 }  // namespace nasr
