@@ -1,11 +1,11 @@
-"""CLI: the `infer` and `rtf` actions of nafx-springrev
+"""CLI: the `infer`, `rtf` and `ir` actions of nafx-springrev
 (src/neural_audio_spring_reverb/__main__.py:5-184) on the B200 engine.
 The other actions (train, eval, download, wrap, ...) are not part of this package."""
 import argparse
 
 import torch
 
-ACTIONS = ["infer", "rtf"]
+ACTIONS = ["infer", "rtf", "ir"]
 
 
 def main(argv=None):
@@ -15,6 +15,7 @@ def main(argv=None):
     parser.add_argument("--device", type=str, default=None, help="cuda:N (default: cuda:0)")
     parser.add_argument("-c", "--checkpoint", type=str, default=None)
     parser.add_argument("-i", "--input", type=str, default=None)
+    parser.add_argument("--duration", type=float, default=5.0, help="sweep length in seconds (ir)")
     args = parser.parse_args(argv)
 
     if args.device is None or args.device == "auto":
@@ -34,6 +35,9 @@ def main(argv=None):
     elif args.action == "rtf":
         from .rtf import measure_rtf
         measure_rtf(args)
+    elif args.action == "ir":
+        from .tools.ir_model import measure_model_ir
+        measure_model_ir(args)
 
 
 if __name__ == "__main__":

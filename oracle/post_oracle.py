@@ -64,3 +64,17 @@ def postprocess_reference_fp32(pred, sample_rate, cutoff_freq=20.0):
     x = x.reshape(-1).unsqueeze(0)
     x /= torch.max(torch.abs(x))
     return x
+
+
+def deconvolve_direct(sweep_output, inverse_filter):
+    """tools/ir_model.py:128-146 of the reference, restated with numpy / scipy in float64 (direct convolution)."""
+    from scipy import signal
+    a = np.asarray(sweep_output, dtype=np.float64).reshape(-1).copy()
+    b = np.asarray(inverse_filter, dtype=np.float64).reshape(-1).copy()
+    a = a - np.mean(a)
+    a /= np.max(np.abs(a))
+    b /= np.max(np.abs(b))
+    ir = signal.convolve(a, b, mode="full", method="direct")
+    ir = ir - np.mean(ir)
+    ir /= np.max(np.abs(ir))
+    return ir

@@ -169,3 +169,17 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_ir_signals():
+    """tests/golden/ir/ir_signals_ref.npz: sweep, inverse filter and reference IR of the reference's own
+    tools/ir_signals.py:generate_reference(0.05 s, 48 kHz) (float64), run in this container."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "ref_ir_signals", "/root/reference/src/neural_audio_spring_reverb/tools/ir_signals.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    sweep, inv, ref_ir = ref.generate_reference(0.05, 48000)
+    out = Path(__file__).resolve().parent / "ir"
+    out.mkdir(exist_ok=True)
+    np.savez_compressed(out / "ir_signals_ref.npz", sweep=sweep, inv=inv, ref_ir=ref_ir)

@@ -1,6 +1,7 @@
 """GPU: the CUDA path (through the Python surface -> C ABI) against the reference's
 golden vectors and against the oracle on seeded inputs. Tolerance: BASELINE.json
 north_star, max|y - y_ref| <= 1e-4 * max|y_ref| per clip, fp32."""
+import numpy as np
 import pytest
 import torch
 
@@ -336,3 +337,43 @@ def test_batch_slicing_under_small_workspace(monkeypatch):
     ref = O.forward(sd, O.config_dilations(cfg), x, cond)
     assert rel_err(y, ref) <= REL_TOL
     m.release_engine()
+
+
+def test_ir_deconvolution_matches_direct_convolution():
+    """tools/ir_model.py:128-146: the reference's scipy direct convolution (float64) against the cuFFT float64 path."""
+    from oracle import post_oracle as P
+    from neural_audio_spring_reverb_b200.tools.ir_model import deconvolve
+    from neural_audio_spring_reverb_b200.tools.ir_signals import generate_reference
+    sweep, inv, _ = generate_reference(0.25, 48000)               # 12 000 samples: direct convolution in ~1 s
+    rng = np.random.default_rng(0)
+    out = np.convolve(sweep, np.exp(-np.arange(3000) / 400.0) * rng.standard_normal(3000))[: len(sweep)] + 0.01
+    ref = P.deconvolve_direct(out, inv)
+    got = deconvolve(out, inv, DEV).cpu().numpy()
+    assert got.shape == ref.shape == (2 * len(sweep) - 1,)
+    assert np.abs(got - ref).max() <= 1e-9
+
+
+def test_measure_model_ir_end_to_end(tmp_path):
+    """`ir` action (tools/ir_model.py:97-175): sweep -> engine -> device post-processing -> deconvolution; the same
+    chain on the oracles (CPU forward, fp64 post-processing, scipy direct convolution)."""
+    import types
+    from oracle import post_oracle as P
+    from neural_audio_spring_reverb_b200.tools.ir_model import measure_model_ir
+    from neural_audio_spring_reverb_b200.tools.ir_signals import generate_reference
+    meta, _, sd = load_golden("ckpt_TCN_egfxset_20240229_002014_48kHz")
+    c = meta["cfg"]
+    config = dict(name="TCN", model_type="TCN", cond_dim=2, c0=0.0, c1=0.0, in_ch=1, out_ch=1, n_channels=c["n_channels"],
+                  n_layers=c["n_blocks"], dilation_growth=c["dilation_growth"], kernel_size=c["kernel_size"],
+                  sample_rate=48000, batch_size=16, bit_depth=24)
+    ck = tmp_path / "tcn.pt"
+    torch.save({"label": "t", "timestamp": "0", "model_state_dict": sd, "optimizer_state_dict": {},
+                "scheduler_state_dict": {}, "config_state_dict": config}, ck)
+    args = types.SimpleNamespace(checkpoint=str(ck), device=torch.device(DEV), audio_dir=str(tmp_path), duration=0.25)
+    ir = measure_model_ir(args)
+    sweep, inv, _ = generate_reference(0.25, 48000)
+    assert tuple(ir.shape) == (1, 2 * len(sweep) - 1) and abs(float(ir.abs().max()) - 1.0) < 1e-6
+    x = torch.as_tensor(sweep.reshape(16, 1, -1), dtype=torch.float32)
+    y = O.forward(sd, meta["dilations"], x, torch.zeros(16, 2))
+    ref = P.deconvolve_direct(P.postprocess(y, 48000).reshape(-1).numpy(), inv)
+    assert np.abs(ir[0].numpy().astype(np.float64) - ref).max() <= 5e-4
+    assert (tmp_path / "IR_models" / "tcn_IR.wav").exists()

@@ -126,3 +126,18 @@ def test_weight_blob_order_matches_c_oracle_order():
         m = build_model(cfg, sd, "cpu")
         ob = c_oracle.blob_from_state(sd, cfg["n_blocks"], cfg["arch"] == "GCN")
         assert torch.equal(m.weight_blob(), torch.from_numpy(ob))
+
+
+def test_ir_signals_match_reference_fixture():
+    """tools/ir_signals.py against the arrays the reference's own generate_reference produced
+    (tests/golden/ir/ir_signals_ref.npz, made by tests/golden/make_golden.py:make_ir_signals)."""
+    import numpy as np
+    from pathlib import Path
+    from neural_audio_spring_reverb_b200.tools.ir_signals import generate_reference
+    z = np.load(Path(__file__).resolve().parent / "golden" / "ir" / "ir_signals_ref.npz")
+    sweep, inv, ref_ir = generate_reference(0.05, 48000, with_reference=True)
+    assert np.array_equal(sweep, z["sweep"]) and np.array_equal(inv, z["inv"])
+    assert np.allclose(ref_ir, z["ref_ir"], rtol=0, atol=1e-12)
+    # sweep * inverse filter is (close to) an impulse: the peak dominates
+    peak = np.abs(ref_ir).max()
+    assert np.abs(ref_ir).argmax() == len(sweep) - 1 and np.median(np.abs(ref_ir)) < 0.05 * peak
