@@ -102,6 +102,17 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// cudaFuncSetAttribute is per device: one bit per device in a per-kernel mask (several engines on different GPUs in one
+// process).  Returns true when the attribute still has to be set on the current device.
+inline bool attr_needed_on_this_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return true;
+  if ((mask >> dev) & 1ull) return false;
+  mask |= 1ull << dev;
+  return true;
+}
+
 // ---- packed fp32x2 epilogue pieces shared by the tensor-core kernels (sm_100 FFMA2 / FMUL2 / FADD2) ----
 // PReLU with one slope a (tcn.py:65): y > 0 ? y : a*y  ==  max(y, a*y) for a <= 1, min(y, a*y) for a > 1 (exact).
 __device__ __forceinline__ float2 prelu2(float2 y, float2 slope2, bool slope_le1) {

@@ -170,7 +170,10 @@ static cudaError_t launch_fb(const BlockArgs& a, const float* w0, int sm_count, 
                                        (size_t)a.Cin * (H + FB_ROWS));
   if (smem > 100 * 1024) return cudaErrorNotSupported;
   auto kern = first_block_kernel<ARCH, C>;
-  static size_t configured = 0;
+  static size_t configured_dev[64] = {0};   // per device: the attribute is per (function, device)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t& configured = configured_dev[dev & 63];
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;

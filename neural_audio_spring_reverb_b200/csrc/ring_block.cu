@@ -778,12 +778,11 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   }
 
   cudaError_t err;
-  static bool attr_set[2] = {false, false};
+  static unsigned long long attr_set[2] = {0, 0};
   const void* fn = L.arch == 0 ? (const void*)ring_block_kernel<0> : (const void*)ring_block_kernel<1>;
-  if (!attr_set[L.arch]) {
+  if (attr_needed_on_this_device(attr_set[L.arch])) {
     err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (err != cudaSuccess) return err;
-    attr_set[L.arch] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);

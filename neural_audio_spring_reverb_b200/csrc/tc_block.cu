@@ -554,19 +554,17 @@ cudaError_t launch_tc_block(const TcLaunch& L, cudaStream_t s) {
   const size_t smem = tc_smem_bytes(L.arch, a.k, R);
   cudaError_t err;
   if (L.arch == 0) {
-    static bool set0 = false;
-    if (!set0) {
+    static unsigned long long set0 = 0;
+    if (attr_needed_on_this_device(set0)) {
       err = cudaFuncSetAttribute(tc_block_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (err != cudaSuccess) return err;
-      set0 = true;
     }
     tc_block_kernel<0><<<(unsigned)grid, tc_threads<0>(), smem, s>>>(in_map, w_map, a);
   } else {
-    static bool set1 = false;
-    if (!set1) {
+    static unsigned long long set1 = 0;
+    if (attr_needed_on_this_device(set1)) {
       err = cudaFuncSetAttribute(tc_block_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (err != cudaSuccess) return err;
-      set1 = true;
     }
     tc_block_kernel<1><<<(unsigned)grid, tc_threads<1>(), smem, s>>>(in_map, w_map, a);
   }

@@ -527,11 +527,10 @@ cudaError_t launch_toep_block(const ToepLaunch& L, cudaStream_t s) {
 #undef NASR_TOEP_PICK
   if (!fn) return cudaErrorNotSupported;
   const size_t smem = tp_smem_bytes();
-  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
-  if (!attr_set[fi]) {
+  static unsigned long long attr_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (attr_needed_on_this_device(attr_set[fi])) {
     cudaError_t err = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    attr_set[fi] = true;
   }
   const long long ntiles = ((a.T + 127) / 128) * a.B;
   long long grid = L.sm_count < ntiles ? L.sm_count : ntiles;
