@@ -86,6 +86,18 @@ cudaError_t launch_copy_rows(const void* src, long long src_clip_stride, long lo
                              void* dst, long long dst_clip_stride, long long dst_row0,
                              long long n_rows, int row_bytes, int B, cudaStream_t s);
 
+// several (segmented) byte copies in one launch; n_bytes per segment must be a multiple of 4
+#define NASR_MULTI_COPY_MAX 64
+struct CopyJob {
+  const char* src;
+  char* dst;
+  long long src_stride, dst_stride;   // bytes between segments
+  long long n_bytes;                  // bytes per segment
+  int segs;
+  int vec;                            // filled in by launch_copy_multi
+};
+cudaError_t launch_copy_multi(const CopyJob* jobs, int n, cudaStream_t s);
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   int sz = valid ? 16 : 0;

@@ -854,7 +854,9 @@ int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev, int B, 
       e->launches += 1;
     }
   }
-  // carry: rows [Tc, Tc + hist) -> [0, hist) of every plane
+  // carry: rows [Tc, Tc + hist) -> [0, hist) of every plane.  Planes whose chunk is at least as long as the history
+  // (source and destination do not overlap) are moved by ONE batched copy launch; shorter chunks go through scratch.
+  std::vector<CopyJob> jobs;
   for (int i = 0; i < n; ++i) {
     const BlockState& bs = e->blocks[i];
     if (bs.hist == 0) continue;
@@ -862,7 +864,15 @@ int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev, int B, 
     const long long stride = (i == 0) ? rows * 4 : rows * rb;
     const int rbytes = (i == 0) ? 4 : (int)rb;
     const int segs = (i == 0) ? B * in_ch : B;
-    if (Tc >= bs.hist) {
+    if (Tc >= bs.hist && (int)jobs.size() < NASR_MULTI_COPY_MAX) {
+      CopyJob j{};
+      j.src = (const char*)e->splane[i].p + Tc * rbytes;
+      j.dst = (char*)e->splane[i].p;
+      j.src_stride = stride; j.dst_stride = stride;
+      j.n_bytes = bs.hist * rbytes;
+      j.segs = segs;
+      jobs.push_back(j);
+    } else if (Tc >= bs.hist) {
       NASR_CUDA(e, launch_copy_rows(e->splane[i].p, stride, Tc, e->splane[i].p, stride, 0, bs.hist, rbytes, segs, s));
       e->launches += 1;
     } else {
@@ -875,6 +885,10 @@ int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev, int B, 
       NASR_CUDA(e, launch_copy_rows(e->scratch.p, bs.hist * rbytes, 0, e->splane[i].p, stride, 0, bs.hist, rbytes, segs, s));
       e->launches += 2;
     }
+  }
+  if (!jobs.empty()) {
+    NASR_CUDA(e, launch_copy_multi(jobs.data(), (int)jobs.size(), s));
+    e->launches += 1;
   }
   return NASR_OK;
 }

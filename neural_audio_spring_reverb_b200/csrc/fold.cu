@@ -142,4 +142,55 @@ cudaError_t launch_copy_rows(const void* src, long long src_clip_stride, long lo
   return cudaGetLastError();
 }
 
+// Several row copies in one launch (the streaming carry of every block's history, wrapper.py:23-30): blockIdx.y walks
+// (copy, segment) pairs, blockIdx.x strides over the bytes.
+struct MultiCopy {
+  int n;
+  int seg_begin[NASR_MULTI_COPY_MAX + 1];   // prefix sums of the segment counts
+  CopyJob job[NASR_MULTI_COPY_MAX];
+};
+
+__global__ void copy_multi_kernel(const __grid_constant__ MultiCopy mc) {
+  int j = 0;
+  while (j + 1 < mc.n && (int)blockIdx.y >= mc.seg_begin[j + 1]) ++j;
+  const CopyJob& c = mc.job[j];
+  const int seg = blockIdx.y - mc.seg_begin[j];
+  const char* s = c.src + (long long)seg * c.src_stride;
+  char* d = c.dst + (long long)seg * c.dst_stride;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  if (c.vec == 16) {
+    const long long n = c.n_bytes / 16;
+    for (long long i = i0; i < n; i += step) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(s)[i];
+  } else {
+    const long long n = c.n_bytes / 4;
+    for (long long i = i0; i < n; i += step) reinterpret_cast<uint32_t*>(d)[i] = reinterpret_cast<const uint32_t*>(s)[i];
+  }
+}
+
+cudaError_t launch_copy_multi(const CopyJob* jobs, int n, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  if (n > NASR_MULTI_COPY_MAX) return cudaErrorInvalidValue;
+  MultiCopy mc{};
+  mc.n = n;
+  long long max_bytes = 0;
+  int segs = 0;
+  for (int i = 0; i < n; ++i) {
+    mc.job[i] = jobs[i];
+    const bool a16 = (((uintptr_t)jobs[i].src | (uintptr_t)jobs[i].dst | (uintptr_t)jobs[i].src_stride |
+                       (uintptr_t)jobs[i].dst_stride | (uintptr_t)jobs[i].n_bytes) & 15) == 0;
+    mc.job[i].vec = a16 ? 16 : 4;
+    mc.seg_begin[i] = segs;
+    segs += jobs[i].segs;
+    if (jobs[i].n_bytes > max_bytes) max_bytes = jobs[i].n_bytes;
+  }
+  mc.seg_begin[n] = segs;
+  if (segs <= 0 || max_bytes <= 0) return cudaSuccess;
+  long long gx = (max_bytes / 16 + 255) / 256;
+  if (gx > 256) gx = 256;
+  if (gx < 1) gx = 1;
+  copy_multi_kernel<<<dim3((unsigned)gx, (unsigned)segs), 256, 0, s>>>(mc);
+  return cudaGetLastError();
+}
+
 }  // namespace nasr

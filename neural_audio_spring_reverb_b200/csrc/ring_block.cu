@@ -58,6 +58,19 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// TMA prefetch of a tile into L2 (no shared memory, no barrier): takes the HBM latency out of the load that follows
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -191,6 +204,13 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
       Span s;
       for (long long sp = sp0; s.set(a, sp); sp += sp_stride) {
         for (int i = -km1; i < s.nsteps; ++i) {
+          if (a.l2_prefetch > 0 && i + a.l2_prefetch < s.nsteps) {
+            // planes that do not fit L2 (large batches): pull the tile of a few steps ahead into L2 now; the ring itself
+            // only covers stages - 2 steps of latency, which mixed read / write HBM traffic exceeds
+            const int ip = i + a.l2_prefetch;
+            if (a.mode == 0) tma_prefetch_4d(&in_map, 0, (int)(a.in_row0 + (long long)ip * a.d), (int)(s.m * a.G), s.b);
+            else tma_prefetch_3d(&in_map, 0, (int)(a.in_row0 + (s.m * a.n + ip) * a.d + 128LL * s.l), s.b);
+          }
           mbar_wait(&empty[st], (empty_phase >> st) & 1u);
           empty_phase ^= 1u << st;
           mbar_arrive_expect_tx(&full[st], tile_bytes);
@@ -544,8 +564,15 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           const int rsw = (NCH == 8) ? (rl & 7) : ((rl >> 1) & 3);
           const uint4 val = *reinterpret_cast<const uint4*>(stage + rl * (NCH * 16) + ((my_c ^ rsw) * 16));
           const long long t = t0 + offq[q];
-          if (((okm >> q) & 1u) && t < a.T)
-            *reinterpret_cast<uint4*>(out_clip + (a.out_row0 + t) * 128LL + cbyte) = val;
+          if (((okm >> q) & 1u) && t < a.T && !(a.dbg & 16)) {   // dbg 16 (dev): everything but the global stores
+            uint4* gp = reinterpret_cast<uint4*>(out_clip + (a.out_row0 + t) * 128LL + cbyte);
+            if (a.dbg & 32)
+              asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+            else if (a.dbg & 64)
+              asm volatile("st.global.wt.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+            else
+              *gp = val;
+          } else if ((a.dbg & 16) && val.x == 0x12345678u) *a.sat_flag = 2u;
         }
         __syncwarp();
       }
@@ -728,6 +755,7 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("NASR_RB_DBG"); dbg = e ? atoi(e) : 0; }
     a.dbg = dbg;
+    a.l2_prefetch = (dbg & 128) ? 8 : 0;
     a.dbg_buf = nullptr;
     if (dbg & 8) {   // dev: per-CTA %globaltimer stamps, read back with ring_debug_stamps()
       static unsigned long long* buf = nullptr;

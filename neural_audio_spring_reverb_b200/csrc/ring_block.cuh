@@ -40,8 +40,9 @@ struct RingArgs {
   const float* wout;       // [out_ch][32]
   int out_ch, final_tanh;
   unsigned int* sat_flag;
+  int l2_prefetch;         // > 0: TMA-prefetch the input tile of that many steps ahead into L2
   unsigned long long* dbg_buf;   // dev only: per-CTA timeline stamps
-  int dbg;                 // dev only (NASR_RB_DBG): 1 = epilogue drains without math/stores, 2 = no MMAs, 4 = no zeroing
+  int dbg;                 // dev only (NASR_RB_DBG): 1 = epilogue drains without math/stores, 2 = no MMAs, 4 = no zeroing, 8 = timeline stamps, 16 = no global stores
 };
 
 struct RingMapCache {
