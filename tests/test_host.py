@@ -141,3 +141,27 @@ def test_ir_signals_match_reference_fixture():
     # sweep * inverse filter is (close to) an impulse: the peak dominates
     peak = np.abs(ref_ir).max()
     assert np.abs(ref_ir).argmax() == len(sweep) - 1 and np.median(np.abs(ref_ir)) < 0.05 * peak
+
+
+def test_postprocess_argument_checks_without_a_device():
+    """nasr_postprocess validates its arguments before touching the device; on a box without a GPU a valid call
+    fails with NASR_ERR_CUDA instead of computing anything on the CPU."""
+    import ctypes as C
+    import numpy as np
+    lib = _native.load_library()
+    assert lib.nasr_postprocess_workspace_bytes(0, 100) == 0
+    assert lib.nasr_postprocess_workspace_bytes(16, 30000) == 256 + 2 * 16 * 16 * ((30000 + 63) // 64)
+    b = np.array([1.0, -2.0, 1.0], dtype=np.float32)
+    a = np.array([1.0, -1.9, 0.9], dtype=np.float32)
+    a0 = np.array([0.0, -1.9, 0.9], dtype=np.float32)
+    dummy = C.c_void_p(256)      # non-NULL, never dereferenced on the host
+    inval = _native.NASR_ERR_INVALID
+    assert lib.nasr_postprocess(None, dummy, 1, 10, b.ctypes.data, a.ctypes.data, 1, dummy, 1 << 20, None) == inval
+    assert lib.nasr_postprocess(dummy, dummy, 0, 10, b.ctypes.data, a.ctypes.data, 1, dummy, 1 << 20, None) == inval
+    assert lib.nasr_postprocess(dummy, dummy, 1, 10, b.ctypes.data, a.ctypes.data, 1, dummy, 8, None) == inval      # workspace
+    assert lib.nasr_postprocess(dummy, dummy, 1, 10, b.ctypes.data, a0.ctypes.data, 1, dummy, 1 << 20, None) == inval  # a0 == 0
+    assert lib.nasr_postprocess(dummy, dummy, 1, 0, b.ctypes.data, a.ctypes.data, 1, dummy, 1 << 20, None) == _native.NASR_OK
+    import torch
+    if not torch.cuda.is_available():
+        rc = lib.nasr_postprocess(dummy, dummy, 1, 10, b.ctypes.data, a.ctypes.data, 1, dummy, 1 << 20, None)
+        assert rc == _native.NASR_ERR_CUDA
