@@ -71,6 +71,13 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, 
                : "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -137,7 +144,8 @@ struct Span {
 
 template <int ARCH>
 __global__ void __launch_bounds__((4 * RB_ESETS + 2) * 32, 1)
-ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map, const RingArgs a) {
+ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map,
+                  const __grid_constant__ CUtensorMap out_map, const RingArgs a) {
   constexpr int ESETS = RB_ESETS;
   constexpr int EPI_WARPS = 4 * ESETS, PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
   constexpr int NO = (ARCH == 1) ? 16 : 32;   // output channels per thread row
@@ -426,6 +434,13 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           if (128LL * s.l + offq[q] < a.d) okm |= 1u << q;
       }
       uint8_t* out_clip = reinterpret_cast<uint8_t*>(a.out) + (long long)s.b * a.out_clip_stride * (a.out_fmt == FMT_SPLIT16 ? 2 : 4);
+      // TMA store of the staged rows (a.tma_out): only where every row of every tile of the span is a real sample
+      // (span inside the clip, full 128-row lane), so that the view's per-dimension bounds never have to clip
+      bool span_tma = false;
+      if (ARCH == 0 && a.tma_out) {
+        if (a.mode == 0) span_tma = (s.m + 1) * a.G * a.S <= a.T;
+        else span_tma = 128LL * (s.l + 1) <= a.d;
+      }
       for (int i = 0; i < s.nsteps; ++i, ++e) {
         if ((int)(e % ESETS) != eset) continue;
         const long long t0 = t_span + (long long)i * a.d;
@@ -447,6 +462,11 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           if (lane == 0) mbar_arrive(drained);
           if (u[0] == 0x12345678u && ok) *a.sat_flag = 2u;
           continue;
+        }
+        // the previous step's TMA store (if any) must have finished reading the staging tile
+        if (ARCH == 0 && a.tma_out) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
         }
         const int wsw = (NCH == 8) ? (lane & 7) : ((lane >> 1) & 3);
         uint8_t* srow = stage + lane * (NCH * 16);
@@ -556,6 +576,22 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           }
           stage16(o, 0, 2);   // staged group row: [hi 16 ch (chunks 0-1) | lo 16 ch (chunks 2-3)] or 4 fp32 chunks
         }
+        if (ARCH == 0 && span_tma && (a.mode == 0 || t0 + 128 <= a.T)) {
+          // ---- one TMA store per warp: its 32 staged rows (SWIZZLE_128B = the staging XOR pattern) ----
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (a.mode == 0) {
+              // rows 32*quad .. +32 of the tile: d >= 32: part of group (32*quad)/d; d < 32: 32/d whole groups
+              const int gq = (32 * quad) / a.d, rq = (32 * quad) % a.d;
+              tma_store_4d(&out_map, stage, 0, (int)(a.out_row0 + (long long)i * a.d + rq), (int)(s.m * a.G + gq), s.b);
+            } else {
+              tma_store_3d(&out_map, stage, 0, (int)(a.out_row0 + t0 + 32 * quad), s.b);
+            }
+            tma_store_commit();
+          }
+          continue;
+        }
         __syncwarp();
         // ---- coalesced stores: 8 (4) lanes per row ----
 #pragma unroll
@@ -577,6 +613,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         __syncwarp();
       }
     }
+    if (ARCH == 0 && a.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (threadIdx.x == 0) rb_stamp(a, 8);
   }
 
@@ -799,6 +836,32 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
     c->in = L.in; c->in_rows = L.in_rows; c->in_stride = L.in_clip_stride_elems; c->B = a.B;
     c->mode = a.mode; c->d = a.d; c->S = a.S; c->in_row0 = a.in_row0;
   }
+  CUtensorMap& out_map = *reinterpret_cast<CUtensorMap*>(c->out_map);
+  {
+    // TMA store path: TCN, 128-byte plane rows, and tile rows that a warp's 32-row box can address
+    static int tma_env = -1;
+    if (tma_env < 0) { const char* ev = getenv("NASR_TMA_STORE"); tma_env = ev ? atoi(ev) : 0; }   // off until measured
+    const bool pow2 = (a.d & (a.d - 1)) == 0;
+    a.tma_out = tma_env && L.arch == 0 && (a.out_fmt == FMT_SPLIT16 || a.out_fmt == FMT_CL) &&
+                (a.mode == 1 || (pow2 && a.d <= 64)) ? 1 : 0;
+    if (a.tma_out) {
+      const long long stride16 = a.out_clip_stride * (a.out_fmt == FMT_SPLIT16 ? 1 : 2);   // 16-bit elements between clips
+      if (c->out != a.out || c->out_rows != a.out_rows || c->out_stride != stride16 || c->out_B != a.B ||
+          c->out_mode != a.mode || c->out_d != a.d || c->out_S != a.S || c->out_row0 != a.out_row0) {
+        bool ok;
+        if (a.mode == 0) {
+          const uint32_t br = a.d < 32 ? a.d : 32, bg = a.d < 32 ? 32 / a.d : 1;
+          ok = make_group_map(&out_map, a.out, (uint64_t)(a.out_row0 + a.S + a.d), (uint64_t)((a.out_rows + a.S - 1) / a.S),
+                              (uint64_t)a.B, (uint64_t)a.S, (uint64_t)stride16, br, bg);
+        } else {
+          ok = make_plane_map(&out_map, a.out, 64, (uint64_t)a.out_rows, (uint64_t)a.B, (uint64_t)stride16, 32);
+        }
+        if (!ok) return cudaErrorInvalidValue;
+        c->out = a.out; c->out_rows = a.out_rows; c->out_stride = stride16; c->out_B = a.B;
+        c->out_mode = a.mode; c->out_d = a.d; c->out_S = a.S; c->out_row0 = a.out_row0;
+      }
+    }
+  }
   if (c->w != L.wpacked || c->NS != a.NS) {
     const uint64_t rows = (uint64_t)n_grp * a.NS * 32;
     if (!make_plane_map(&w_map, L.wpacked, 64, rows, 1, rows * 64, 32)) return cudaErrorInvalidValue;
@@ -822,8 +885,8 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = L.pdl ? 1 : 0;
-  if (L.arch == 0) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<0>, in_map, w_map, a);
-  else err = cudaLaunchKernelEx(&cfg, ring_block_kernel<1>, in_map, w_map, a);
+  if (L.arch == 0) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<0>, in_map, w_map, out_map, a);
+  else err = cudaLaunchKernelEx(&cfg, ring_block_kernel<1>, in_map, w_map, out_map, a);
   if (err != cudaSuccess) return err;
   return cudaGetLastError();
 }

@@ -40,6 +40,7 @@ struct RingArgs {
   const float* wout;       // [out_ch][32]
   int out_ch, final_tanh;
   unsigned int* sat_flag;
+  int tma_out;             // rows leave through TMA stores of the staging tiles where the geometry allows
   int l2_prefetch;         // > 0: TMA-prefetch the input tile of that many steps ahead into L2
   unsigned long long* dbg_buf;   // dev only: per-CTA timeline stamps
   int dbg;                 // dev only (NASR_RB_DBG): 1 = epilogue drains without math/stores, 2 = no MMAs, 4 = no zeroing, 8 = timeline stamps, 16 = no global stores
@@ -48,6 +49,10 @@ struct RingArgs {
 struct RingMapCache {
   alignas(64) unsigned char in_map[128];
   alignas(64) unsigned char w_map[128];
+  alignas(64) unsigned char out_map[128];
+  const void* out = nullptr;
+  long long out_rows = -1, out_stride = -1, out_S = -1, out_row0 = -1;
+  int out_B = -1, out_mode = -1, out_d = -1;
   const void* in = nullptr;
   const void* w = nullptr;
   long long in_rows = -1, in_stride = -1, S = -1, in_row0 = -1;
