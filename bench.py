@@ -273,17 +273,20 @@ def main():
     value = world * B * T * args.steps / total_s
 
     # ---- end to end through the public API with host buffers ----
-    for _ in range(3):
+    # every call is synchronous (H2D, forward, result written to the pinned output, stream sync); at least 50 calls so
+    # that a single host hiccup (allocator, scheduler) does not decide a short run
+    n_e2e = max(args.steps, 50)
+    for _ in range(5):
         model(x_host, cond_host)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(n_e2e):
         y_host = model(x_host, cond_host)
     torch.cuda.synchronize(dev)
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * T * args.steps / float(e2e_s)
+    e2e_value = world * B * T * n_e2e / float(e2e_s)
 
     # ---- live per-kernel timing for the roofline (rank 0) ----
     line = None
@@ -315,16 +318,23 @@ def main():
         # The tcgen05 kernels compute an fp32-grade product as 3 fp16 products (xh*wh + xh*wl + xl*wh), so the
         # tensor pipe executes 3x the algorithmic FLOPs; its roof for this work is measured fp16/bf16 peak / 3.
         issued = 3.0 * tfs
-        tensor_frac = issued / pk["bf16"]
+        # MEASURED_PEAKS.json carries a burst figure (kernel timed alone) and a sustained one (kernel inside a long,
+        # power-capped run).  The per-launch times above are taken right after hundreds of back-to-back forwards: when the
+        # SM clock sampled under that load sits well below its maximum, the sustained figure is the matching denominator.
+        sustained = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and
+                         clocks["sm_mhz"] < 0.9 * clocks["sm_max_mhz"])
+        bf16_peak = pk["bf16_sustained"] if sustained else pk["bf16"]
+        tensor_frac = issued / bf16_peak
         if tensor_path and tensor_frac >= hbm_frac:
-            roof = dict(bound="tensor", achieved=issued, peak=pk["bf16"], unit="TFLOP/s", frac=tensor_frac, traffic=None,
+            roof = dict(bound="tensor", achieved=issued, peak=bf16_peak, unit="TFLOP/s", frac=tensor_frac, traffic=None,
                         note="achieved = fp16 tensor FLOPs executed (3 per algorithmic fp32-grade FLOP: split-fp16 "
                              "product); algorithmic_tflops is the SURVEY 8d figure; hbm_* gives the HBM view of the same launch")
         else:
             roof = dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=hbm_frac, traffic=None)
         roof.update(kernel=("ring_block_kernel" if ring_path else "tc_block_kernel") if tensor_path
                     else "generic_block_kernel (fp32 FFMA)",
-                    peak_source=pk["source"], launch_ms=dom_ms, hbm_gbs=gbs, hbm_frac=hbm_frac,
+                    peak_source=pk["source"] + (", sustained bf16 figure (SM clock under load %.0f of %.0f MHz)" % (clocks["sm_mhz"], clocks["sm_max_mhz"]) if sustained else ", burst bf16 figure"),
+                    frac_of_burst_peak=issued / pk["bf16"], launch_ms=dom_ms, hbm_gbs=gbs, hbm_frac=hbm_frac,
                     algorithmic_tflops=tfs, issued_fp16_tflops=issued if tensor_path else None,
                     fp32_ffma_frac_of_75tf=tfs / 75.0,
                     block_ms=block_ms, block_paths=paths,
@@ -359,7 +369,7 @@ def main():
                     config=dict(workload=args.workload, arch=arch, **kw, clip_seconds=T / SR, clips_per_gpu=B,
                                 global_clips=world * B, sample_rate=SR, l2="flushed between timed iterations (256 MiB write)",
                                 parallelism=f"clips sharded over {world} GPU(s), NCCL weight broadcast only"),
-                    e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=int(x_host.numel() * 4 + cond_host.numel() * 4),
+                    e2e=dict(value=e2e_value, unit="samples/s", steps=n_e2e, h2d_bytes_per_step=int(x_host.numel() * 4 + cond_host.numel() * 4),
                              d2h_bytes_per_step=int(y_host.numel() * 4)),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)
         print(json.dumps(line), flush=True)

@@ -840,7 +840,7 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   {
     // TMA store path: TCN, 128-byte plane rows, and tile rows that a warp's 32-row box can address
     static int tma_env = -1;
-    if (tma_env < 0) { const char* ev = getenv("NASR_TMA_STORE"); tma_env = ev ? atoi(ev) : 0; }   // off until measured
+    if (tma_env < 0) { const char* ev = getenv("NASR_TMA_STORE"); tma_env = ev ? atoi(ev) : 1; }
     const bool pow2 = (a.d & (a.d - 1)) == 0;
     a.tma_out = tma_env && L.arch == 0 && (a.out_fmt == FMT_SPLIT16 || a.out_fmt == FMT_CL) &&
                 (a.mode == 1 || (pow2 && a.d <= 64)) ? 1 : 0;
