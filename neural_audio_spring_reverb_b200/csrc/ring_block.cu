@@ -12,11 +12,14 @@
 // once, so ONE instruction per 16-channel slice multiplies the tile with the stacked weights
 // [V_0; V_1; ...; V_{k-1}; R] (N up to 256 per instruction) and scatters into a ring of k + 1
 // accumulator slots of 32 TMEM columns: slot (i + s) mod (k+1) collects y_{i+s}; the extra slot
-// takes the 1x1 residual R x_i.  After step i the slot of y_i is complete and is drained by
-// the epilogue while step i + 1 runs; the slot it frees is the one step i + 1 starts afresh.
-// Each input tile is fetched from shared memory 6 times per step (2 channel slices x 3 product
-// terms) instead of 6 times per tap, which lifts the kernel from the operand-fetch limit of
-// small-N MMAs (tc_block.cu) to the tensor-pipe math limit.
+// takes the 1x1 residual R x_i.  After step i the slot of y_i is complete; the epilogue loads it
+// (and the residual), writes zeros back and signals the issuer - the two slots it read are exactly
+// the two that step i + 1 starts, so in steady state every MMA accumulates: 12 instructions of
+// M128 N256 K16 per 128 samples (2 fixed chunks of the slot ring x 6 product terms / slices; the
+// weights are stored with a wrapping copy so that a chunk always maps to contiguous blocks).
+// Each input tile is fetched from shared memory 12 times per step instead of 6 times per tap,
+// which lifts the kernel from the operand-fetch limit of small-N MMAs (tc_block.cu) to the
+// tensor-pipe math limit.  Planes hold value * kActScale (common.cuh).
 //
 // Tiles whose rows are d apart: for d >= 128 a tile is 128 consecutive rows of one period
 // (mode L, lanes beyond d masked); for d < 128 a tile is G = 128/d groups of d consecutive rows,
@@ -34,7 +37,8 @@
 #include <cstdlib>
 
 #ifndef RB_ESETS
-#define RB_ESETS 2        // epilogue warp sets (3 was measured: no gain at B = 8, one input stage less) (4 warps each); set e drains steps with index % ESETS == e
+#define RB_ESETS 2        // epilogue warp sets of 4 warps; set e drains the steps with index % ESETS == e
+                          // (3 sets were measured: no gain at B = 8, and they cost one input stage)
 #endif
 
 namespace nasr {

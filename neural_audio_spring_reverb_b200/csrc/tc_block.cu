@@ -7,7 +7,7 @@
 //   D[t, w] = sum_taps sum_ci  X[t - shift_tap, ci] * W_tap[w, ci]        M = 128 samples, N = conv width, K = 32 ch
 //
 // * Activations travel between blocks as SPLIT16 rows: 32 x fp16 "hi" then 32 x fp16 "lo"
-//   (value = hi + lo, 22+ significant bits, same 128 bytes per sample as fp32).  One row is
+//   (value * kActScale = hi + lo, 22+ significant bits, same 128 bytes per sample as fp32).  One row is
 //   exactly one SWIZZLE_128B line, so a TMA box of 128 rows is a ready-made K-major UMMA
 //   A operand, and a causal tap shift is nothing but a different start row of the
 //   descriptor (probe/umma_probe.cu: any row offset works with base_offset = 0).
