@@ -1,0 +1,28 @@
+"""CPU: the reference arm of bench.py (the oracle port timed on the host cores) prints the contract's JSON line."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_reference_arm_prints_contract_line():
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--cpu-seconds", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["higher_is_better"] is True
+    assert line["steps"] == 2 and line["value"] > 0 and line["vs_baseline"] is None
+    assert line["metric"].startswith("audio samples/sec")
+    assert line["config"]["workload"] == "cfg2"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == dict(value=line["value"], unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    import os
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                       capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
