@@ -100,3 +100,39 @@ def test_plan_rejects_too_many_taps():
     lib = _native.load_library()
     out = (C.c_int64 * 16)()
     assert lib.nasr_debug_ring_plan(0, 16, 2, 1, 1000, 0, 148, out) != 0     # 17 slots do not fit TMEM
+
+
+def tma_store_rows(p, d, m, i, quad, out_row0):
+    """Plane rows (per clip) the epilogue's TMA store of warp `quad` at step i of span m covers, in staged-row order
+    (ring_block.cu: tma_store_4d / tma_store_3d branch)."""
+    if p["mode"] == 0:
+        gq, rq = (32 * quad) // d, (32 * quad) % d
+        br, bg = (d, 32 // d) if d < 32 else (32, 1)
+        r0, j0 = out_row0 + i * d + rq, m * p["G"] + gq
+        assert r0 + br <= out_row0 + p["S"] + d                      # r extent of the output view
+        return ((j0 + np.arange(bg))[:, None] * p["S"] + (r0 + np.arange(br))[None, :]).reshape(-1)
+    raise AssertionError("mode L uses the plain 3-D plane map")
+
+
+@pytest.mark.parametrize("d,T,out_row0", [(2, 5000, 0), (4, 9000, 0), (16, 20000, 14 * 16), (32, 4099, 0), (64, 30000, 0)])
+def test_tma_store_boxes_address_the_epilogue_rows(d, T, out_row0):
+    """mode S, power-of-two dilation: the 4-D store box of each epilogue warp lands exactly on the rows
+    out_row0 + t of its 32 staged samples, for every span that lies inside the clip."""
+    k, B = 15, 1
+    p = plan(0, k, d, B, T, out_row0)
+    assert p["mode"] == 0
+    rows = np.arange(128)
+    jg, rr = rows // d, rows % d
+    checked = 0
+    for m in range(p["spans_per_strip"]):
+        if (m + 1) * p["G"] * p["S"] > T:
+            continue                                                  # span_tma is false: ordinary stores
+        nsteps = min(-((T - m * p["G"] * p["S"]) // -d), p["n"])
+        for i in range(nsteps):
+            t = m * p["G"] * p["S"] + jg * p["S"] + rr + i * d
+            for quad in range(4):
+                got = tma_store_rows(p, d, m, i, quad, out_row0)
+                assert np.array_equal(got, out_row0 + t[32 * quad: 32 * quad + 32]), (m, i, quad)
+                assert got.max() < out_row0 + T                       # never past the clip: no clipping needed
+                checked += 1
+    assert checked > 0 or p["spans_per_strip"] == 1
