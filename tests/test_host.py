@@ -165,3 +165,30 @@ def test_postprocess_argument_checks_without_a_device():
     if not torch.cuda.is_available():
         rc = lib.nasr_postprocess(dummy, dummy, 1, 10, b.ctypes.data, a.ctypes.data, 1, dummy, 1 << 20, None)
         assert rc == _native.NASR_ERR_CUDA
+
+
+def test_wav_io_without_torchcodec(tmp_path):
+    """inference.py's WAV reader / writer work without TorchCodec (torchaudio.load needs it in recent releases):
+    24-bit PCM - the format of the reference's audio assets - and the float32 files the writer produces."""
+    import wave
+    import numpy as np
+    import torch
+    from neural_audio_spring_reverb_b200.inference import _read_wav, _write_wav
+    rng = np.random.default_rng(0)
+    ints = rng.integers(-(1 << 23), 1 << 23, size=4800, dtype=np.int64)
+    raw = b"".join(int(v & 0xFFFFFF).to_bytes(3, "little") for v in ints)
+    p24 = tmp_path / "in24.wav"
+    with wave.open(str(p24), "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(3)
+        w.setframerate(48000)
+        w.writeframes(raw)
+    x, sr = _read_wav(str(p24))
+    assert sr == 48000 and tuple(x.shape) == (1, 4800) and x.dtype == torch.float32
+    assert np.allclose(x[0].numpy(), ints / float(1 << 23), atol=1e-7)
+    out = tmp_path / "out.wav"
+    y = torch.linspace(-1, 1, 1000).unsqueeze(0)
+    _write_wav(str(out), y, 16000)
+    z, sr2 = _read_wav(str(out))
+    assert sr2 == 16000 and tuple(z.shape) == (1, 1000)
+    assert float((z - y).abs().max()) <= 1.0 / 32768 + 1e-7     # torchaudio may store 16-bit PCM, scipy float32
