@@ -131,6 +131,15 @@ NASR_API int nasr_set_cond(nasr_engine* e, const float* cond_dev, int B, void* s
 NASR_API int nasr_forward(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T,
                  void* stream);
 
+/* nasr_forward that is correct for ANY input range, like the reference forward (tcn.py:150-155 has no range limit):
+ * runs the call, waits for `stream`, and if an inter-block activation left the fp16 range of the tensor-core path
+ * (see nasr_saturated) runs it again on the fp32 kernels before returning. *redone (may be NULL) = 1 if it did.
+ * This is what the Python forward uses for device tensors; nasr_forward stays fully asynchronous. */
+NASR_API int nasr_forward_checked(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T,
+                         void* stream, int* redone);
+/* how many calls on this handle were redone on the fp32 kernels so far (nasr_forward_host, nasr_forward_checked) */
+NASR_API int64_t nasr_sat_fallbacks(const nasr_engine* e);
+
 /* nasr_forward with a CUDA-event pair around every block launch on `stream`;
  * waits for completion and writes the n_blocks device durations (ms) to block_ms.
  * Used by bench.py for the live per-kernel roofline numbers. */
@@ -186,6 +195,7 @@ NASR_API const char* nasr_version(void);
 
 /* dev only: per-CTA timeline stamps of the last ring-kernel launch made with NASR_RB_DBG=8 (tools/ring_timeline.py) */
 NASR_API int nasr_debug_ring_stamps(unsigned long long* host, int max_ctas);
+NASR_API int nasr_debug_ring_steps(unsigned long long* host);   /* same launch: per-step stamps of CTA 0, host[4][64] */
 NASR_API int nasr_debug_toep_stamps(unsigned long long* host, int n);   /* NASR_TOEP_DBG=8, tools/toep_timeline.py */
 /* dev / tests: host-side launch plan of the accumulator-ring kernel (no device needed); out16 = {mode, G, L, n, S, NP,
  * spans_per_strip, total_spans, grid, stages, NS, NW, tmem_cols, smem_bytes, n_grp, rext}; 0 on success */

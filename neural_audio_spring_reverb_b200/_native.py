@@ -20,10 +20,10 @@ LIB_PATH = Path(os.environ.get("NASR_LIB") or Path(__file__).resolve().parent / 
 # every symbol include/nasr_b200.h declares
 EXPORTS = (
     "nasr_weight_count", "nasr_engine_create", "nasr_engine_destroy", "nasr_last_error",
-    "nasr_set_cond", "nasr_forward", "nasr_forward_profiled", "nasr_saturated", "nasr_forward_host", "nasr_stream_reset",
+    "nasr_set_cond", "nasr_forward", "nasr_forward_checked", "nasr_sat_fallbacks", "nasr_forward_profiled", "nasr_saturated", "nasr_forward_host", "nasr_stream_reset",
     "nasr_forward_chunk", "nasr_block_forward", "nasr_workspace_bytes",
     "nasr_receptive_field", "nasr_launch_count", "nasr_block_path", "nasr_version",
-    "nasr_postprocess", "nasr_postprocess_workspace_bytes", "nasr_debug_ring_stamps", "nasr_debug_ring_plan", "nasr_debug_toep_stamps",
+    "nasr_postprocess", "nasr_postprocess_workspace_bytes", "nasr_debug_ring_stamps", "nasr_debug_ring_steps", "nasr_debug_ring_plan", "nasr_debug_toep_stamps",
 )
 
 
@@ -63,6 +63,10 @@ def load_library():
     lib.nasr_set_cond.argtypes = [vp, f32p, i32, vp]
     lib.nasr_forward.restype = i32
     lib.nasr_forward.argtypes = [vp, f32p, f32p, i32, i64, vp]
+    lib.nasr_forward_checked.restype = i32
+    lib.nasr_forward_checked.argtypes = [vp, f32p, f32p, i32, i64, vp, C.POINTER(C.c_int)]
+    lib.nasr_sat_fallbacks.restype = i64
+    lib.nasr_sat_fallbacks.argtypes = [vp]
     lib.nasr_forward_profiled.restype = i32
     lib.nasr_forward_profiled.argtypes = [vp, f32p, f32p, i32, i64, vp, C.c_void_p]
     lib.nasr_saturated.restype = i32
@@ -91,6 +95,8 @@ def load_library():
     lib.nasr_postprocess.argtypes = [f32p, f32p, i32, i64, C.c_void_p, C.c_void_p, i32, vp, C.c_size_t, vp]
     lib.nasr_debug_ring_plan.restype = i32
     lib.nasr_debug_ring_plan.argtypes = [i32, i32, i32, i32, i64, i64, i32, C.c_void_p]
+    lib.nasr_debug_ring_steps.restype = i32
+    lib.nasr_debug_ring_steps.argtypes = [C.c_void_p]
     lib.nasr_debug_ring_stamps.restype = i32
     lib.nasr_debug_ring_stamps.argtypes = [C.c_void_p, i32]
     _lib = lib
@@ -154,6 +160,17 @@ class Engine:
 
     def forward(self, x_ptr: int, y_ptr: int, B: int, T: int, stream: int = 0):
         self._ck(self._lib.nasr_forward(self._h, x_ptr, y_ptr, B, T, stream or None), "nasr_forward")
+
+    def forward_checked(self, x_ptr: int, y_ptr: int, B: int, T: int, stream: int = 0) -> bool:
+        """Forward that is valid for any input range: waits for the stream and redoes the call on the fp32 kernels if
+        an activation left the fp16 range of the tensor-core path. Returns True if it had to."""
+        redone = C.c_int(0)
+        self._ck(self._lib.nasr_forward_checked(self._h, x_ptr, y_ptr, B, T, stream or None, C.byref(redone)),
+                 "nasr_forward_checked")
+        return bool(redone.value)
+
+    def sat_fallbacks(self) -> int:
+        return int(self._lib.nasr_sat_fallbacks(self._h))
 
     def forward_profiled(self, x_ptr: int, y_ptr: int, B: int, T: int, stream: int = 0):
         """-> list of per-block device milliseconds (CUDA events on `stream`)."""

@@ -53,7 +53,19 @@ struct BlockArgs {
   int out_ch;
   int final_tanh;
   unsigned int* sat_flag;  // set to 1 when a value written as SPLIT16 had to be clamped to +-65504
+  unsigned long long* prof;   // nasr_forward_profiled: {earliest CTA start, latest CTA end} of this launch (%globaltimer, ns), or NULL
 };
+
+// per-launch time stamps for nasr_forward_profiled: they do not disturb the stream (an event between two launches would
+// serialise them and lose the programmatic-dependent-launch overlap that the real forward has)
+__device__ __forceinline__ void prof_stamp(unsigned long long* prof, int end) {
+  if (prof) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (end) atomicMax(prof + 1, t);
+    else atomicMin(prof, t);
+  }
+}
 
 cudaError_t launch_generic_block(const BlockArgs& a, int sm_count, cudaStream_t s);
 // first block (Cin = in_ch <= 4): w0 = conv weights [k][Cin][W] in original channel order;
@@ -79,7 +91,7 @@ cudaError_t launch_fold(const FoldArgs* blocks_dev, const float* cond, int n_blo
 // out_net on a channels-last fp32 plane (when the last block's kernel cannot fuse it)
 cudaError_t launch_out_net(const float* plane, long long plane_clip_stride, long long row0, int Cp, int C, const float* wout,
                            int out_ch, int final_tanh, float* y, long long y_clip_stride, long long y_rows, long long y_row0,
-                           int B, long long T, int sm_count, cudaStream_t s);
+                           int B, long long T, int sm_count, cudaStream_t s, unsigned long long* prof = nullptr);
 
 // streaming helpers
 cudaError_t launch_copy_rows(const void* src, long long src_clip_stride, long long src_row0,

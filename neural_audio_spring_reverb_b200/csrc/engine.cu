@@ -19,6 +19,9 @@ using namespace nasr;
 
 namespace {
 
+constexpr int kSatWords = 1024;
+constexpr int kMaxClips = 65535;   // clips (x in_ch for the streaming copies) ride in gridDim.y of the helper kernels
+
 thread_local std::string g_create_error;
 
 struct DevBuf {
@@ -61,8 +64,13 @@ struct nasr_engine {
   // "a SPLIT16 write saturated during the last forward": lives in mapped pinned host memory, so
   // kernels raise it over PCIe only in the rare bad case and the host reads it after a stream
   // sync without any copy. sat_flag is the device-side alias of sat_host.
-  unsigned int* sat_flag = nullptr;
-  volatile unsigned int* sat_host = nullptr;
+  // One word per call, used round-robin (kSatWords of them): a call clears ITS word from the host before it enqueues
+  // anything, so work of earlier calls that is still in flight (it raises the word of its own call) can neither be
+  // lost nor leak into this call's verdict; a word is reused only kSatWords calls later, far beyond the launch queue.
+  unsigned int* sat_flag = nullptr;            // device alias of sat_host[0]
+  volatile unsigned int* sat_host = nullptr;   // [kSatWords]
+  unsigned int* sat_cur = nullptr;             // device alias of the current call's word
+  uint64_t sat_gen = 0;
   DevBuf plane[2];
   // streaming
   int streamB = 0;
@@ -76,6 +84,9 @@ struct nasr_engine {
   mutable std::string err;
   int64_t launches = 0;
   int64_t sat_fallbacks = 0;
+  // nasr_forward_profiled: per-launch {start, end} %globaltimer stamps, [n_blocks + 1] pairs (last = split out_net)
+  unsigned long long* prof_dev = nullptr;
+  bool prof_on = false;
   bool pdl = true;   // NASR_PDL=0 turns programmatic dependent launch off (dev)
   bool zero_copy = true;   // NASR_ZEROCOPY=0: always stage y through device memory on the host-tensor path
 };
@@ -85,6 +96,22 @@ namespace {
 int fail(nasr_engine* e, int code, const std::string& msg) {
   if (e) e->err = msg; else g_create_error = msg;
   return code;
+}
+
+// start of a call that may raise the saturation flag: pick and clear its word
+inline void sat_begin(nasr_engine* e) {
+  e->sat_gen += 1;
+  const size_t idx = (size_t)(e->sat_gen % kSatWords);
+  e->sat_host[idx] = 0;
+  e->sat_cur = e->sat_flag + idx;
+}
+inline volatile unsigned int& sat_word(nasr_engine* e) { return e->sat_host[e->sat_gen % kSatWords]; }
+
+inline int check_clips(nasr_engine* e, int B) {
+  if (B < 1) return fail(e, NASR_ERR_INVALID, "B must be >= 1");
+  if ((long long)B * (e->desc.in_ch > 1 ? e->desc.in_ch : 1) > kMaxClips)
+    return fail(e, NASR_ERR_INVALID, "B * in_ch > 65535 clips per call is unsupported: split the batch");
+  return NASR_OK;
 }
 
 #define NASR_CUDA(e, call)                                                              \
@@ -190,7 +217,8 @@ BlockArgs make_args(const nasr_engine* e, int i, int B, bool tc = true) {
   const BlockState& bs = e->blocks[i];
   const int n = (int)e->blocks.size();
   BlockArgs a{};
-  a.sat_flag = e->sat_flag;
+  a.sat_flag = e->sat_cur;
+  a.prof = e->prof_on ? e->prof_dev + 2 * i : nullptr;
   a.B = B;
   a.arch = e->desc.arch;
   a.Cin = bs.Cin; a.Cinp = bs.Cinp; a.W = bs.W; a.Wp = bs.Wp; a.Cout = bs.Cout; a.Coutp = bs.Coutp;
@@ -220,7 +248,7 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
     t.out_row0 = a.out_row0; t.in_row0 = a.in_row0; t.B = a.B; t.T = a.T; t.k = a.k; t.d = a.d;
     t.scale = a.scale; t.shift = a.shift; t.slope = a.slope;
     t.inv_sw = bs.inv_sw * kActInv; t.inv_sr = bs.inv_sr * kActInv;   // the input plane holds value * kActScale
-    t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_flag;
+    t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_cur; t.prof = a.prof;
     err = launch_tc_block(L, s);
   } else if (allow_tc && tc_chain && bs.path == 2) {
     RingLaunch L{};
@@ -232,7 +260,7 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
     t.out_row0 = a.out_row0; t.in_row0 = a.in_row0; t.B = a.B; t.T = a.T; t.k = a.k; t.d = a.d;
     t.scale = a.scale; t.shift = a.shift; t.ld_affine = bs.Wp; t.slope = a.slope;
     t.inv_sw = bs.inv_sw * kActInv; t.inv_sr = bs.inv_sr * kActInv;   // the input plane holds value * kActScale
-    t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_flag;
+    t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_cur; t.prof = a.prof;
     err = launch_ring_block(L, s);
   } else {
     err = cudaErrorNotSupported;
@@ -246,7 +274,7 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
       t.B = a.B; t.T = a.T; t.Cin = a.Cin; t.k = a.k; t.d = a.d;
       t.scale = a.scale; t.shift = a.shift; t.ld_affine = bs.Wp; t.slope = a.slope;
       t.inv_sw = bs.toep_inv_sw * kActInv; t.inv_sr = bs.toep_inv_sr * kActInv;   // the Toeplitz tile holds x * kActScale
-      t.sat_flag = e->sat_flag;
+      t.sat_flag = e->sat_cur; t.prof = a.prof;
       err = launch_toep_block(L, s);
     }
     if (err == cudaErrorNotSupported && bs.w0 && allow_tc) err = launch_first_block(a, bs.w0, e->sm_count, s);
@@ -294,6 +322,7 @@ void nasr_engine_destroy(nasr_engine* e) {
     for (auto& b : e->blocks) free_block(b);
     if (e->wout) cudaFree(e->wout);
     if (e->fold_dev) cudaFree(e->fold_dev);
+    if (e->prof_dev) cudaFree(e->prof_dev);
     if (e->sat_host) cudaFreeHost((void*)e->sat_host);
     release(e->plane[0]); release(e->plane[1]);
     for (auto& p : e->splane) release(p);
@@ -456,10 +485,13 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
   }
   if (rc == NASR_OK) {
     cudaError_t err = cudaMalloc((void**)&e->fold_dev, sizeof(FoldArgs) * n);
-    if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->sat_host, sizeof(unsigned int), cudaHostAllocMapped);
+    if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->sat_host, sizeof(unsigned int) * kSatWords, cudaHostAllocMapped);
     if (err == cudaSuccess) err = cudaHostGetDevicePointer((void**)&e->sat_flag, (void*)e->sat_host, 0);
     if (err != cudaSuccess) rc = fail(nullptr, NASR_ERR_NOMEM, "fold args / flag allocation failed");
-    else *e->sat_host = 0;
+    else {
+      for (int q = 0; q < kSatWords; ++q) e->sat_host[q] = 0;
+      e->sat_cur = e->sat_flag;
+    }
   }
   if (rc != NASR_OK) {
     std::string keep = g_create_error;
@@ -480,7 +512,7 @@ int nasr_set_cond(nasr_engine* e, const float* cond_dev, int B, void* stream) {
 // cond_inline_host: host copy of cond small enough to ride in the fold kernel's parameters (host-tensor path)
 static int set_cond_impl(nasr_engine* e, const float* cond_dev, const float* cond_inline_host, int B, void* stream) {
   if (!e) return NASR_ERR_INVALID;
-  if (B < 1) return fail(e, NASR_ERR_INVALID, "B must be >= 1");
+  if (int rcB = check_clips(e, B)) return rcB;
   if (e->desc.has_film && e->desc.cond_dim > 0 && !cond_dev && !cond_inline_host)
     return fail(e, NASR_ERR_INVALID, "cond is NULL but cond_dim > 0");
   DeviceGuard guard(e->device);
@@ -489,17 +521,31 @@ static int set_cond_impl(nasr_engine* e, const float* cond_dev, const float* con
   if (B > e->condCap) {
     // grow scale/shift; in-flight work on other streams must not still be reading them
     NASR_CUDA(e, cudaDeviceSynchronize());
-    for (auto& b : e->blocks) {
+    // allocate every new table first and swap them in only when all succeeded: a failure half way must not leave
+    // blocks with null / dangling tables behind a stale condCap
+    std::vector<float*> ns(n, nullptr), nh(n, nullptr);
+    cudaError_t aerr = cudaSuccess;
+    for (int i = 0; i < n && aerr == cudaSuccess; ++i) {
+      const size_t bytes = (size_t)B * e->blocks[i].Wp * sizeof(float);
+      aerr = cudaMalloc((void**)&ns[i], bytes);
+      if (aerr == cudaSuccess) aerr = cudaMalloc((void**)&nh[i], bytes);
+      if (aerr == cudaSuccess) aerr = cudaMemset(ns[i], 0, bytes);
+      if (aerr == cudaSuccess) aerr = cudaMemset(nh[i], 0, bytes);
+    }
+    if (aerr != cudaSuccess) {
+      for (int i = 0; i < n; ++i) { if (ns[i]) cudaFree(ns[i]); if (nh[i]) cudaFree(nh[i]); }
+      return fail(e, aerr == cudaErrorMemoryAllocation ? NASR_ERR_NOMEM : NASR_ERR_CUDA,
+                  std::string("scale/shift allocation: ") + cudaGetErrorString(aerr));
+    }
+    e->fold_valid = false;
+    e->condB = 0;
+    for (int i = 0; i < n; ++i) {
+      BlockState& b = e->blocks[i];
       if (b.scale) cudaFree(b.scale);
       if (b.shift) cudaFree(b.shift);
-      b.scale = b.shift = nullptr;
-      NASR_CUDA(e, cudaMalloc((void**)&b.scale, (size_t)B * b.Wp * sizeof(float)));
-      NASR_CUDA(e, cudaMalloc((void**)&b.shift, (size_t)B * b.Wp * sizeof(float)));
-      NASR_CUDA(e, cudaMemset(b.scale, 0, (size_t)B * b.Wp * sizeof(float)));
-      NASR_CUDA(e, cudaMemset(b.shift, 0, (size_t)B * b.Wp * sizeof(float)));
+      b.scale = ns[i]; b.shift = nh[i];
     }
     e->condCap = B;
-    e->fold_valid = false;
   }
   int maxW = 0;
   for (const auto& b : e->blocks) maxW = b.W > maxW ? b.W : maxW;
@@ -523,7 +569,7 @@ static int set_cond_impl(nasr_engine* e, const float* cond_dev, const float* con
 }
 
 static int forward_slice(nasr_engine* e, const float* x, float* y, int b0, int B, int64_t T, cudaStream_t s,
-                         cudaEvent_t* ev = nullptr, bool tc = true) {
+                         bool tc = true) {
   const int n = (int)e->blocks.size();
   const size_t row_bytes = plane_row_bytes(e);
   const long long plane_elems = (long long)T * e->Cp;  // fp32 elements per clip
@@ -548,23 +594,24 @@ static int forward_slice(nasr_engine* e, const float* x, float* y, int b0, int B
       a.out_clip_stride = (a.out_fmt == FMT_SPLIT16) ? plane_elems * 2 : plane_elems;
       a.out_rows = T; a.out_row0 = 0;
     }
-    if (ev) cudaEventRecord(ev[i], s);
     int rc = launch_block(e, a, i, s, /*allow_tc=*/true, /*tc_chain=*/tc);
     if (rc != NASR_OK) return rc;
     if (split_out) {
       cudaError_t err = launch_out_net((const float*)e->plane[i & 1].p, plane_elems, 0, e->Cp, e->C, e->wout, e->desc.out_ch,
-                                       e->desc.final_tanh, y, (long long)e->desc.out_ch * T, T, 0, B, T, e->sm_count, s);
+                                       e->desc.final_tanh, y, (long long)e->desc.out_ch * T, T, 0, B, T, e->sm_count, s,
+                                       e->prof_on ? e->prof_dev + 2 * n : nullptr);
       if (err != cudaSuccess) return fail(e, NASR_ERR_CUDA, std::string("out_net launch: ") + cudaGetErrorString(err));
       e->launches += 1;
     }
   }
-  if (ev) cudaEventRecord(ev[n], s);
   (void)row_bytes;
   return NASR_OK;
 }
 
 static int forward_impl(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T, void* stream,
                         float* block_ms, bool tc = true);
+
+int64_t nasr_sat_fallbacks(const nasr_engine* e) { return e ? e->sat_fallbacks : 0; }
 
 int nasr_forward(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T, void* stream) {
   return forward_impl(e, x_dev, y_dev, B, T, stream, nullptr);
@@ -575,7 +622,25 @@ int nasr_saturated(nasr_engine* e, void* stream) {
   DeviceGuard guard(e->device);
   cudaStream_t s = (cudaStream_t)stream;
   NASR_CUDA(e, cudaStreamSynchronize(s));
-  return *e->sat_host ? 1 : 0;
+  return sat_word(e) ? 1 : 0;
+}
+
+int nasr_forward_checked(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T, void* stream, int* redone) {
+  if (redone) *redone = 0;
+  int rc = forward_impl(e, x_dev, y_dev, B, T, stream, nullptr);
+  if (rc != NASR_OK || T == 0) return rc;
+  DeviceGuard guard(e->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  NASR_CUDA(e, cudaStreamSynchronize(s));
+  if (!sat_word(e)) return NASR_OK;
+  // an activation left the fp16 range of the SPLIT16 planes: same call again on the fp32 kernels (tcn.py:150-155 has
+  // no input-range limit, so neither may the drop-in)
+  e->sat_fallbacks += 1;
+  rc = forward_impl(e, x_dev, y_dev, B, T, stream, nullptr, /*tc=*/false);
+  if (rc != NASR_OK) return rc;
+  sat_word(e) = 1;
+  if (redone) *redone = 1;
+  return NASR_OK;
 }
 
 int nasr_forward_profiled(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T, void* stream,
@@ -589,6 +654,7 @@ static int forward_impl(nasr_engine* e, const float* x_dev, float* y_dev, int B,
   if (!e) return NASR_ERR_INVALID;
   if (!x_dev || !y_dev) return fail(e, NASR_ERR_INVALID, "x or y is NULL");
   if (B < 1 || T < 0) return fail(e, NASR_ERR_INVALID, "B must be >= 1 and T >= 0");
+  if (int rcB = check_clips(e, B)) return rcB;
   if (T == 0) return NASR_OK;
   DeviceGuard guard(e->device);
   cudaStream_t s = (cudaStream_t)stream;
@@ -617,30 +683,42 @@ static int forward_impl(nasr_engine* e, const float* x_dev, float* y_dev, int B,
       }
     }
   }
-  // Cleared from the host: safe because work that could still raise the flag belongs to an
-  // earlier forward, whose verdict the caller either already read or chose to skip.
-  *e->sat_host = 0;
-  std::vector<cudaEvent_t> ev;
+  sat_begin(e);   // this call's own flag word (earlier calls still in flight raise theirs)
+  // Profiled mode: the forward runs exactly as always (same launches, programmatic dependent launch intact); every
+  // kernel stamps %globaltimer at its earliest CTA start and latest CTA end.  block_ms[i] = end_i - end_{i-1} (block
+  // 0: from its own start), so the figures add up to the forward's duration instead of double-counting overlap.
+  std::vector<unsigned long long> stamps;
   if (block_ms) {
-    ev.resize(n + 1);
-    for (auto& q : ev) NASR_CUDA(e, cudaEventCreate(&q));
+    if (!e->prof_dev) NASR_CUDA(e, cudaMalloc((void**)&e->prof_dev, sizeof(unsigned long long) * 2 * (NASR_MAX_BLOCKS + 1)));
+    stamps.resize((size_t)2 * (n + 1));
     for (int i = 0; i < n; ++i) block_ms[i] = 0.f;
   }
   int rc = NASR_OK;
   for (int b0 = 0; b0 < B && rc == NASR_OK; b0 += slice) {
     const int nb = (B - b0 < slice) ? B - b0 : slice;
-    rc = forward_slice(e, x_dev + (size_t)b0 * e->desc.in_ch * T, y_dev + (size_t)b0 * e->desc.out_ch * T, b0, nb, T, s,
-                       block_ms ? ev.data() : nullptr, tc);
+    if (block_ms) {
+      for (int i = 0; i <= n; ++i) { stamps[2 * i] = ~0ull; stamps[2 * i + 1] = 0ull; }
+      NASR_CUDA(e, cudaMemcpyAsync(e->prof_dev, stamps.data(), stamps.size() * sizeof(unsigned long long),
+                                   cudaMemcpyHostToDevice, s));
+      NASR_CUDA(e, cudaStreamSynchronize(s));   // pageable source: make sure the copy is not what the first kernel waits for
+      e->prof_on = true;
+    }
+    rc = forward_slice(e, x_dev + (size_t)b0 * e->desc.in_ch * T, y_dev + (size_t)b0 * e->desc.out_ch * T, b0, nb, T, s, tc);
+    e->prof_on = false;
     if (block_ms && rc == NASR_OK) {
-      if (cudaEventSynchronize(ev[n]) != cudaSuccess) rc = fail(e, NASR_ERR_CUDA, "event synchronize failed");
+      if (cudaMemcpyAsync(stamps.data(), e->prof_dev, stamps.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s) !=
+              cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+        rc = fail(e, NASR_ERR_CUDA, "profile read-back failed");
+      unsigned long long prev = stamps[0];
       for (int i = 0; i < n && rc == NASR_OK; ++i) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
-        block_ms[i] += ms;
+        unsigned long long end = stamps[2 * i + 1];
+        if (i == n - 1 && stamps[2 * n + 1] > end) end = stamps[2 * n + 1];   // split out_net belongs to the last block
+        if (end == 0ull || stamps[2 * i] == ~0ull) { rc = fail(e, NASR_ERR_STATE, "a block kernel left no profile stamp"); break; }
+        block_ms[i] += end > prev ? (float)((double)(end - prev) * 1e-6) : 0.f;
+        if (end > prev) prev = end;
       }
     }
   }
-  for (auto& q : ev) cudaEventDestroy(q);
   return rc;
 }
 
@@ -715,14 +793,14 @@ int nasr_forward_host(nasr_engine* e, const float* x_host, const float* cond_hos
             us(h0, h1), us(h1, h2), us(h2, h3), us(h3, h4), us(h0, h4), d01 * 1e3, d12 * 1e3, d23 * 1e3);
     for (auto& q : ev) cudaEventDestroy(q);
   }
-  if (*e->sat_host) {
+  if (sat_word(e)) {
     // an activation exceeded the fp16 range of the SPLIT16 planes: redo this call on the fp32 kernels
     e->sat_fallbacks += 1;
     rc = forward_impl(e, (const float*)e->hx.p, (float*)e->hy.p, B, T, stream, nullptr, /*tc=*/false);
     if (rc != NASR_OK) return rc;
     NASR_CUDA(e, cudaMemcpyAsync(y_host, e->hy.p, yb, cudaMemcpyDeviceToHost, s));
     NASR_CUDA(e, cudaStreamSynchronize(s));
-    *e->sat_host = 1;
+    sat_word(e) = 1;   // nasr_saturated() keeps reporting that the tensor-core path did not hold this call
   }
   return NASR_OK;
 }
@@ -747,27 +825,25 @@ static int stream_alloc(nasr_engine* e, int B, long long Tcap, cudaStream_t s, b
       return fail(e, NASR_ERR_NOMEM, std::string("stream plane allocation: ") + cudaGetErrorString(err));
     }
   }
-  for (int i = 0; i < n; ++i) {
+  cudaError_t cerr = cudaSuccess;
+  for (int i = 0; i < n && cerr == cudaSuccess; ++i) {
     const BlockState& b = e->blocks[i];
     if (b.hist == 0) continue;
-    if (i == 0) {
-      const long long old_rows = b.hist + e->streamTcap, new_rows = b.hist + Tcap;
-      if (keep_history)
-        NASR_CUDA(e, launch_copy_rows(e->splane[i].p, old_rows * 4, 0, np[i].p, new_rows * 4, 0, b.hist, 4,
-                                      B * e->desc.in_ch, s));
-      else
-        NASR_CUDA(e, cudaMemsetAsync(np[i].p, 0, np[i].cap, s));
+    const long long rb = (i == 0) ? 4 : (long long)plane_row_bytes(e);
+    const int segs = (i == 0) ? B * e->desc.in_ch : B;
+    const long long old_rows = b.hist + e->streamTcap, new_rows = b.hist + Tcap;
+    if (keep_history) {
+      cerr = launch_copy_rows(e->splane[i].p, old_rows * rb, 0, np[i].p, new_rows * rb, 0, b.hist, (int)rb, segs, s);
+      e->launches += 1;
     } else {
-      const long long rb = (long long)plane_row_bytes(e);
-      const long long old_rows = b.hist + e->streamTcap, new_rows = b.hist + Tcap;
-      if (keep_history)
-        NASR_CUDA(e, launch_copy_rows(e->splane[i].p, old_rows * rb, 0, np[i].p, new_rows * rb, 0, b.hist, (int)rb, B, s));
-      else
-        NASR_CUDA(e, cudaMemsetAsync(np[i].p, 0, np[i].cap, s));
+      cerr = cudaMemsetAsync(np[i].p, 0, np[i].cap, s);
     }
-    if (keep_history) e->launches += 1;
   }
-  NASR_CUDA(e, cudaStreamSynchronize(s));
+  if (cerr == cudaSuccess) cerr = cudaStreamSynchronize(s);
+  if (cerr != cudaSuccess) {   // the old planes (and the stream's history) stay as they were
+    for (auto& q : np) release(q);
+    return fail(e, NASR_ERR_CUDA, std::string("stream plane set-up: ") + cudaGetErrorString(cerr));
+  }
   for (auto& q : e->splane) release(q);
   e->splane = np;
   e->streamB = B;
@@ -777,11 +853,11 @@ static int stream_alloc(nasr_engine* e, int B, long long Tcap, cudaStream_t s, b
 
 int nasr_stream_reset(nasr_engine* e, int B, void* stream) {
   if (!e) return NASR_ERR_INVALID;
-  if (B < 1) return fail(e, NASR_ERR_INVALID, "B must be >= 1");
+  if (int rcB = check_clips(e, B)) return rcB;
   DeviceGuard guard(e->device);
   cudaStream_t s = (cudaStream_t)stream;
   NASR_CUDA(e, cudaStreamSynchronize(s));
-  *e->sat_host = 0;
+  sat_begin(e);
   const long long Tcap = (e->streamB == B && e->streamTcap > 0) ? e->streamTcap : 1024;
   if (e->streamB == B && !e->splane.empty()) {
     for (auto& q : e->splane) NASR_CUDA(e, cudaMemsetAsync(q.p, 0, q.cap, s));
@@ -809,6 +885,7 @@ int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev, int B, 
     int rc = stream_alloc(e, B, Tc, s, true);
     if (rc != NASR_OK) return rc;
   }
+  sat_begin(e);
   const int n = (int)e->blocks.size();
   const long long Tcap = e->streamTcap;
   const long long rb = (long long)plane_row_bytes(e);
@@ -850,7 +927,7 @@ int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev, int B, 
     if (rc != NASR_OK) return rc;
     if (i == n - 1 && bs.split_out) {
       NASR_CUDA(e, launch_out_net((const float*)e->sfinal.p, Tc * e->Cp, 0, e->Cp, e->C, e->wout, e->desc.out_ch,
-                                  e->desc.final_tanh, y_dev, (long long)e->desc.out_ch * Tc, Tc, 0, B, Tc, e->sm_count, s));
+                                  e->desc.final_tanh, y_dev, (long long)e->desc.out_ch * Tc, Tc, 0, B, Tc, e->sm_count, s, nullptr));
       e->launches += 1;
     }
   }
@@ -907,6 +984,7 @@ int nasr_block_forward(nasr_engine* e, int block, const float* x_dev, float* y_d
     if (rc != NASR_OK) return rc;
   }
   const BlockState& bs = e->blocks[block];
+  sat_begin(e);
   BlockArgs a = make_args(e, block, B);
   a.T = T;
   a.in_fmt = FMT_NCT; a.out_fmt = FMT_NCT;
@@ -940,6 +1018,8 @@ int64_t nasr_receptive_field(const nasr_engine* e) {
 int nasr_debug_ring_stamps(unsigned long long* host, int max_ctas) {
   return ring_debug_stamps(host, max_ctas);
 }
+
+int nasr_debug_ring_steps(unsigned long long* host) { return ring_debug_steps(host); }
 
 int nasr_debug_toep_stamps(unsigned long long* host, int n) { return toep_debug_stamps(host, n); }
 

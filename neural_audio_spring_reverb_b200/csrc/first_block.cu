@@ -19,6 +19,7 @@ template <int ARCH, int C>
 __global__ void __launch_bounds__(FB_THREADS, ((ARCH == 1 ? 2 * C : C) > 32 ? 2 : 3)) first_block_kernel(const BlockArgs a, const float* __restrict__ w0) {
   constexpr int W = ARCH == 1 ? 2 * C : C;
   extern __shared__ __align__(16) float fsm[];
+  if (threadIdx.x == 0) prof_stamp(a.prof, 0);
   const int Cin = a.Cin, k = a.k, d = a.d;
   const int H = (k - 1) * d;
   float* stg = fsm;                        // [4 warps][32 rows][C] row staging for the coalesced stores
@@ -158,6 +159,10 @@ __global__ void __launch_bounds__(FB_THREADS, ((ARCH == 1 ? 2 * C : C) > 32 ? 2 
         }
       }
     }
+  }
+  if (a.prof) {
+    __syncthreads();
+    if (threadIdx.x == 0) prof_stamp(a.prof, 1);
   }
 }
 

@@ -61,8 +61,10 @@ cudaError_t launch_fold(const FoldArgs* blocks_dev, const float* cond, int n_blo
 template <int LPR>
 __global__ void out_net_kernel(const float* __restrict__ plane, long long plane_clip_stride, long long row0, int Cp,
                                const float* __restrict__ wout, int out_ch, int final_tanh, float* __restrict__ y,
-                               long long y_clip_stride, long long y_rows, long long y_row0, long long T) {
+                               long long y_clip_stride, long long y_rows, long long y_row0, long long T,
+                               unsigned long long* prof) {
   constexpr int RPI = 32 / LPR;   // rows per load instruction
+  if (threadIdx.x == 0) prof_stamp(prof, 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int b = blockIdx.y;
   const int my_c = lane % LPR, my_r = lane / LPR;
@@ -89,11 +91,15 @@ __global__ void out_net_kernel(const float* __restrict__ plane, long long plane_
         y[(long long)b * y_clip_stride + (long long)o * y_rows + y_row0 + t0 + lane] = final_tanh ? tanhf(mine) : mine;
     }
   }
+  if (prof) {
+    __syncthreads();
+    if (threadIdx.x == 0) prof_stamp(prof, 1);
+  }
 }
 
 cudaError_t launch_out_net(const float* plane, long long plane_clip_stride, long long row0, int Cp, int C, const float* wout,
                            int out_ch, int final_tanh, float* y, long long y_clip_stride, long long y_rows, long long y_row0,
-                           int B, long long T, int sm_count, cudaStream_t s) {
+                           int B, long long T, int sm_count, cudaStream_t s, unsigned long long* prof) {
   (void)C;
   if (B <= 0 || T <= 0) return cudaSuccess;
   if (Cp != 32) return cudaErrorNotSupported;   // only the 32-channel ring kernel needs it
@@ -101,7 +107,7 @@ cudaError_t launch_out_net(const float* plane, long long plane_clip_stride, long
   const long long cap = (long long)sm_count * 8 / B + 1;
   if (gx > cap) gx = cap;
   out_net_kernel<8><<<dim3((unsigned)gx, B), 256, 0, s>>>(plane, plane_clip_stride, row0, Cp, wout, out_ch, final_tanh, y,
-                                                          y_clip_stride, y_rows, y_row0, T);
+                                                          y_clip_stride, y_rows, y_row0, T, prof);
   return cudaGetLastError();
 }
 

@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(512, 1) generic_block_kernel(const BlockArgs a
   constexpr int NCO = (ARCH == 1) ? NC / 2 : NC;   // output channels per thread
   extern __shared__ __align__(16) float smem[];
 
+  if (threadIdx.x == 0) prof_stamp(a.prof, 0);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nthreads = blockDim.x;
@@ -328,6 +329,10 @@ __global__ void __launch_bounds__(512, 1) generic_block_kernel(const BlockArgs a
     }
   }
   cp_async_wait<0>();
+  if (a.prof) {
+    __syncthreads();
+    if (threadIdx.x == 0) prof_stamp(a.prof, 1);
+  }
 }
 
 template <int NC, int CIV, int ARCH>

@@ -122,6 +122,17 @@ __device__ __forceinline__ void rb_stamp(const RingArgs& a, int slot) {
   }
 }
 
+// dev: per-step stamps of CTA 0 (kind 0 = step's MMAs issued, 1 = epilogue drained, 2 = epilogue rows stored / handed to
+// TMA, 3 = input tile requested), 64 steps each, behind the per-CTA area
+constexpr int RB_DBG_CTAS = 1024, RB_DBG_STEPS = 64;
+__device__ __forceinline__ void rb_step_stamp(const RingArgs& a, int kind, int step) {
+  if (a.dbg_buf && blockIdx.x == 0 && step >= 0 && step < RB_DBG_STEPS) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.dbg_buf[(size_t)RB_DBG_CTAS * 16 + kind * RB_DBG_STEPS + step] = t;
+  }
+}
+
 // one span = n consecutive steps of one strip (clip b, lane l)
 struct Span {
   int b, l, nsteps;
@@ -167,18 +178,22 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
   // step e completes on done[e % NDONE]; only epilogue set e % ESETS waits on it, and with NDONE = 2 * ESETS that set
   // sees every completion of the barrier in turn (a parity wait can only tell the current phase from the previous one)
   uint64_t* done = empty + RB_MAX_STAGES;      // [NDONE]  step complete -> epilogue
-  uint64_t* drained = done + NDONE;            // [1]  epilogue has read its slots -> MMA
-  uint64_t* wfull = drained + 1;               // [1]
+  // epilogue(e) has read its slots -> MMA: drained[e & 1].  Two barriers because the issuer consumes the drains strictly in
+  // order but may run up to two steps ahead of them in a span's tail (a parity wait cannot tell phases two apart)
+  uint64_t* drained = done + NDONE;            // [2]
+  uint64_t* wfull = drained + 2;               // [1]
   uint32_t* tmem_slot = (uint32_t*)(wfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int km1 = a.k - 1, NS = a.NS;
 
   if (threadIdx.x == 0) {
+    prof_stamp(a.prof, 0);
     rb_stamp(a, 0);
     for (int i = 0; i < RB_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (uint32_t i = 0; i < NDONE; ++i) mbar_init(&done[i], 1);
-    mbar_init(drained, 4);
+    mbar_init(&drained[0], 4);
+    mbar_init(&drained[1], 4);
     mbar_init(wfull, 1);
     fence_barrier_init();
   }
@@ -239,6 +254,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             const long long row = a.in_row0 + (s.m * a.n + i) * a.d + 128LL * s.l;
             tma_load_3d(ring + (size_t)st * RB_TILE_BYTES, &in_map, &full[st], 0, (int)row, s.b);
           }
+          if (sp == sp0) rb_step_stamp(a, 3, i + km1);
           st = (st + 1 == a.stages) ? 0 : st + 1;
         }
       }
@@ -246,7 +262,10 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     __syncwarp();
   } else if (warp == MMA_WARP) {
     // ================================ MMA issuer (one thread) ================================
+    // (A converged warp with the tcgen05 instructions predicated on one lane was tried: ptxas then wraps every MMA in a
+    // vote / elect / R2UR.BROADCAST loop, which costs more than the plain R2UR moves of the single-thread form.)
     if (rb_elect_one()) {
+      constexpr uint32_t leader_real = 1u;
       constexpr uint32_t idesc0 = make_idesc(FMT_F16, FMT_F16, 128, 0);
       const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t w_lo32 = ((smem_u32(wsm) & 0x3FFFFu) >> 4) | (1u << 16);
@@ -267,18 +286,20 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
       const int h0 = nchunk == 2 ? (NS + 1) / 2 : NS;
       mbar_wait(wfull, 0);
       tc_fence_after();
-      rb_stamp(a, 3);
+      if (leader_real) rb_stamp(a, 3);
       int st = 0;
-      uint32_t full_phase = 0, drain_phase = 0, e = 0;
-      bool pending = false;
-      auto wait_drain = [&]() {
-        if (pending) {
-          mbar_wait(drained, drain_phase);
-          drain_phase ^= 1u;
-          pending = false;
+      uint32_t full_phase = 0, e = 0;     // e = output steps committed so far (global index of the next one)
+      uint32_t drain_seen = 0;            // epilogues 0 .. drain_seen-1 are known to have read their slots
+      auto wait_drain_upto = [&](uint32_t n) {   // consume drains in order until epilogues 0 .. n-1 are done
+        if (drain_seen < n) {
+          do {
+            mbar_wait(&drained[drain_seen & 1u], (drain_seen >> 1) & 1u);
+            ++drain_seen;
+          } while (drain_seen < n);
           tc_fence_after();
         }
       };
+      auto wait_drain = [&]() { wait_drain_upto(e); };   // every epilogue issued so far
       Span s;
       for (long long sp = sp0; s.set(a, sp); sp += sp_stride) {
         // ---- warm-up steps i = -(k-1) .. 0: exact block ranges, slots 0 .. i+k-1 (no wrap); the last
@@ -288,7 +309,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           mbar_wait(&full[st], (full_phase >> st) & 1u);
           full_phase ^= 1u << st;
           tc_fence_after();
-          if (e == 0 && i == -km1) rb_stamp(a, 4);
+          if (e == 0 && i == -km1 && leader_real) rb_stamp(a, 4);
           const uint32_t a_lo = ring_lo + (uint32_t)st * (RB_TILE_BYTES >> 4);
           const int len = i + a.k;                  // blocks -i .. k-1  ->  slots 0 .. len-1
           const int nf = len - 1;                   // slots already started
@@ -302,10 +323,10 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             if (tb > 8) { mma(a_lo, 0, -i, 8, c, 1u); mma(a_lo, 8, -i + 8, tb - 8, c, 1u); }
             else mma(a_lo, 0, -i, tb, c, 1u);
           }
-          umma_commit(&empty[st]);
+          umma_commit_if(&empty[st], leader_real);
+          if (sp == sp0 && leader_real) rb_step_stamp(a, 0, i + km1);
           if (i == 0) {
-            umma_commit(&done[e % NDONE]);
-            pending = true;
+            umma_commit_if(&done[e % NDONE], leader_real);
             ++e;
           }
           st = (st + 1 == a.stages) ? 0 : st + 1;
@@ -313,7 +334,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         // ---- steady state: every block, fixed chunks of the ring; slot (i + b) mod NS <- block b.  The two
         //      slots that start at step i, (i-2) and (i-1) mod NS, were read AND zeroed by epilogue(i-1), so
         //      every instruction accumulates; the chunk that holds them waits for that drain. ----
-        if (e == 1) rb_stamp(a, 5);
+        if (e == 1 && leader_real) rb_stamp(a, 5);
         int islot = 1 % NS;
         for (int i = 1; i < s.nsteps; ++i) {
           mbar_wait(&full[st], (full_phase >> st) & 1u);
@@ -324,7 +345,52 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           const int f2 = f1 >= 1 ? f1 - 1 : f1 - 1 + NS;              // (i-2) mod NS
           // block of slot 0 is (0 - i) mod NS; the weights are stored twice so that a chunk never wraps
           const int bz = islot == 0 ? 0 : NS - islot;
-          if (nchunk == 2) {
+          const int rem = s.nsteps - 1 - i;        // output steps of this span still to come after y_i
+          if (rem < km1 && !(a.dbg & 256)) {
+            // ---- tail of the span: blocks that would only feed outputs past the span's end are skipped (the next
+            //      span's warm-up computes them), so that warm-up + tail together cost one full set of products.
+            //      Needed: the residual (slot f1) and blocks 0..rem (slots i .. i+rem) = rem + 2 consecutive slots
+            //      from f1 (mod NS).  Like the steady state each chunk of the ring gets ONE instruction per product
+            //      term - more, smaller instructions cost more than they save (each has a ~100-cycle floor: operand
+            //      fetch + issue) - but it only spans the hull of the needed slots inside the chunk, or is skipped.
+            //      Slots inside a hull that are not needed hold outputs past the span's end (never read; restarted by
+            //      the next warm-up).  The chunk that holds f1 waits for epilogue(i - 1), which also hands f1 back
+            //      zeroed; f2 = f1 - 1 (that epilogue's residual slot) can only lie inside the hull of f1's own chunk. ----
+            const int cnt = rem + 2;
+            // per chunk [c0, c1): hull [lo, hi) of the needed slots, empty if hi <= lo.  The needed set is
+            // [f1, min(f1 + cnt, NS)) plus [0, f1 + cnt - NS) when it wraps
+            const int e1 = f1 + cnt < NS ? f1 + cnt : NS;
+            const int w1 = f1 + cnt - NS;
+            auto hull = [&](int c0, int c1, int& lo, int& hi) {
+              lo = c1; hi = c0;
+              const int a0 = f1 > c0 ? f1 : c0, a1 = e1 < c1 ? e1 : c1;
+              if (a1 > a0) { lo = a0; hi = a1; }
+              if (w1 > 0) {
+                const int b1 = w1 < c1 ? w1 : c1;
+                if (b1 > c0) { if (c0 < lo) lo = c0; if (b1 > hi) hi = b1; }
+              }
+            };
+            int lo0, hi0, lo1, hi1;
+            hull(0, h0, lo0, hi0);
+            hull(h0, NS, lo1, hi1);           // nchunk == 1: empty
+            auto piece = [&](int lo, int hi) {
+              if (hi > lo) {
+                int b0 = bz + lo;
+                if (b0 >= NS) b0 -= NS;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) mma(a_lo, lo, b0, hi - lo, c, 1u);
+              }
+            };
+            if (nchunk == 2 && f1 >= h0) {    // the chunk of the freshly drained slot goes last
+              piece(lo0, hi0);
+              wait_drain();
+              piece(lo1, hi1);
+            } else {
+              piece(lo1, hi1);
+              wait_drain();
+              piece(lo0, hi0);
+            }
+          } else if (nchunk == 2) {
             const bool fresh0 = f1 < h0 || f2 < h0, fresh1 = f1 >= h0 || f2 >= h0;
             const int b1 = bz + h0 >= NS ? bz + h0 - NS : bz + h0;
             if (!fresh0) {
@@ -349,15 +415,15 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
 #pragma unroll
             for (int c = 0; c < 6; ++c) mma(a_lo, 0, bz, NS, c, 1u);
           }
-          umma_commit(&empty[st]);          // the tile may be overwritten once these MMAs have read it
-          umma_commit(&done[e % NDONE]);    // y_i and its residual are complete
-          pending = true;
+          umma_commit_if(&empty[st], leader_real);          // the tile may be overwritten once these MMAs have read it
+          umma_commit_if(&done[e % NDONE], leader_real);    // y_i and its residual are complete
+          if (sp == sp0 && leader_real) rb_step_stamp(a, 0, i + km1);
           ++e;
           st = (st + 1 == a.stages) ? 0 : st + 1;
           islot = islot + 1 == NS ? 0 : islot + 1;
         }
       }
-      rb_stamp(a, 6);
+      if (leader_real) rb_stamp(a, 6);
     }
     __syncwarp();
   } else {
@@ -411,6 +477,9 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     const bool slope_le1 = a.slope <= 1.0f;
     uint32_t e = 0;
     Span s;
+    // scale / shift come from the fold kernel: with programmatic dependent launch this CTA may be resident while
+    // fold_kernel (two launches back, when block 0's grid leaves SMs free) still writes them
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (long long sp = sp0; s.set(a, sp); sp += sp_stride) {
       const float* sc = a.scale + (long long)s.b * a.ld_affine;
       const float* sh = a.shift + (long long)s.b * a.ld_affine;
@@ -448,7 +517,14 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
       for (int i = 0; i < s.nsteps; ++i, ++e) {
         if ((int)(e % ESETS) != eset) continue;
         const long long t0 = t_span + (long long)i * a.d;
-        const int cslot = i % NS, rslot = (i + NS - 1) % NS;
+        const int cslot = i % NS;
+        const int rslot = (i + NS - 1) % NS;
+        // the step hands its two slots back zeroed: the next step starts new sums in them by accumulating.  A next step
+        // in the span's tail only needs the first one (its residual slot); after the last step nothing is needed (the
+        // next span's warm-up starts every slot itself)
+        const bool zero_c = (a.dbg & 256) || i + 1 < s.nsteps;
+        const bool zero_r = (a.dbg & 256) || (s.nsteps - 2 - i >= km1);
+        uint64_t* drained_e = &drained[e & 1u];
         mbar_wait(&done[e % NDONE], (e / NDONE) & 1u);
         tc_fence_after();
         if (e == 0 && threadIdx.x == 0) rb_stamp(a, 7);
@@ -463,12 +539,14 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(drained);
+          if (lane == 0) mbar_arrive(drained_e);
           if (u[0] == 0x12345678u && ok) *a.sat_flag = 2u;
           continue;
         }
-        // the previous step's TMA store (if any) must have finished reading the staging tile
-        if (ARCH == 0 && a.tma_out) {
+        // the previous step's TMA store (if any) must have finished reading the staging tile before it is rewritten.
+        // The wait sits right before the first staging write, AFTER the TMEM drain: a store that is held up by a busy
+        // memory system (planes larger than L2) must not delay handing the accumulator slots back to the MMA issuer.
+        if (ARCH == 0 && a.tma_out && (a.dbg & 4096)) {   // dev 4096: old position (before the drain)
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
         }
@@ -508,12 +586,15 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           tmem_ld_32x32(lane_base + (uint32_t)(cslot * 32), u);
           tmem_ld_32x32(lane_base + (uint32_t)(rslot * 32), v);
           tmem_ld_wait();
-          tmem_zero_32x32(lane_base + (uint32_t)(cslot * 32));
-          tmem_zero_32x32(lane_base + (uint32_t)(rslot * 32));
-          tmem_st_wait();
+          if (zero_c) {
+            tmem_zero_32x32(lane_base + (uint32_t)(cslot * 32));
+            if (zero_r) tmem_zero_32x32(lane_base + (uint32_t)(rslot * 32));
+            tmem_st_wait();
+          }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(drained);
+          if (lane == 0) mbar_arrive(drained_e);
+          if (quad == 0 && lane == 0 && sp == sp0) rb_step_stamp(a, 1, i + km1);
           // 4 channels: affine -> PReLU -> + residual
           auto out4 = [&](int c, float (&o4)[4]) {
             const float4 s4 = *reinterpret_cast<const float4*>(aff + c);
@@ -546,6 +627,10 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             }
             continue;
           }
+          if (a.tma_out && !(a.dbg & 4096)) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             float o[16];
@@ -564,12 +649,14 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           tmem_ld_32x32(lane_base + (uint32_t)(cslot * 32), u);
           tmem_ld_32x16(lane_base + (uint32_t)(rslot * 32), v);
           tmem_ld_wait();
-          tmem_zero_32x32(lane_base + (uint32_t)(cslot * 32));
-          tmem_zero_32x32(lane_base + (uint32_t)(rslot * 32));
-          tmem_st_wait();
+          if (zero_c) {
+            tmem_zero_32x32(lane_base + (uint32_t)(cslot * 32));
+            if (zero_r) tmem_zero_32x32(lane_base + (uint32_t)(rslot * 32));
+            tmem_st_wait();
+          }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(drained);
+          if (lane == 0) mbar_arrive(drained_e);
           if (a.out_fmt == FMT_FINAL) continue;   // not produced by the GCN groups (engine: split out_net)
           float o[16];
 #pragma unroll
@@ -593,6 +680,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
               tma_store_3d(&out_map, stage, 0, (int)(a.out_row0 + t0 + 32 * quad), s.b);
             }
             tma_store_commit();
+            if (quad == 0 && sp == sp0) rb_step_stamp(a, 2, i + km1);
           }
           continue;
         }
@@ -614,6 +702,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
               *gp = val;
           } else if ((a.dbg & 16) && val.x == 0x12345678u) *a.sat_flag = 2u;
         }
+        if (quad == 0 && lane == 0 && sp == sp0) rb_step_stamp(a, 2, i + km1);
         __syncwarp();
       }
     }
@@ -623,7 +712,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) rb_stamp(a, 9);
+  if (threadIdx.x == 0) { rb_stamp(a, 9); prof_stamp(a.prof, 1); }
   if (warp == PRODUCER_WARP) tmem_dealloc(tmem, (uint32_t)a.tmem_cols);
 }
 
@@ -789,6 +878,15 @@ int ring_debug_stamps(unsigned long long* host, int max_ctas) {
   return n;
 }
 
+// dev: per-step stamps of CTA 0 of the last launch made with NASR_RB_DBG & 8: host[4][64]
+int ring_debug_steps(unsigned long long* host) {
+  if (!g_dbg_buf) return 0;
+  cudaDeviceSynchronize();
+  cudaMemcpy(host, g_dbg_buf + (size_t)RB_DBG_CTAS * 16, (size_t)4 * RB_DBG_STEPS * sizeof(unsigned long long),
+             cudaMemcpyDeviceToHost);
+  return 4 * RB_DBG_STEPS;
+}
+
 cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   RingArgs a = L.a;
   if (a.B <= 0 || a.T <= 0) return cudaSuccess;
@@ -796,12 +894,17 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("NASR_RB_DBG"); dbg = e ? atoi(e) : 0; }
     a.dbg = dbg;
-    a.l2_prefetch = (dbg & 128) ? 8 : 0;
+    {
+      static int pf = -1;
+      if (pf < 0) { const char* e = getenv("NASR_RB_PF"); pf = e ? atoi(e) : 0; }
+      a.l2_prefetch = (dbg & 128) ? 8 : pf;
+    }
     a.dbg_buf = nullptr;
     if (dbg & 8) {   // dev: per-CTA %globaltimer stamps, read back with ring_debug_stamps()
       static unsigned long long* buf = nullptr;
-      if (!buf) { cudaMalloc(&buf, 1024 * 16 * sizeof(unsigned long long)); }
-      cudaMemsetAsync(buf, 0, 1024 * 16 * sizeof(unsigned long long), s);
+      constexpr size_t kDbgWords = (size_t)RB_DBG_CTAS * 16 + 4 * RB_DBG_STEPS;
+      if (!buf) { cudaMalloc(&buf, kDbgWords * sizeof(unsigned long long)); }
+      cudaMemsetAsync(buf, 0, kDbgWords * sizeof(unsigned long long), s);
       a.dbg_buf = buf;
       g_dbg_buf = buf;
     }

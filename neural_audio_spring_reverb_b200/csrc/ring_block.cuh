@@ -42,6 +42,7 @@ struct RingArgs {
   unsigned int* sat_flag;
   int tma_out;             // rows leave through TMA stores of the staging tiles where the geometry allows
   int l2_prefetch;         // > 0: TMA-prefetch the input tile of that many steps ahead into L2
+  unsigned long long* prof;      // nasr_forward_profiled: {start, end} stamps of this launch, or NULL
   unsigned long long* dbg_buf;   // dev only: per-CTA timeline stamps
   int dbg;                 // dev only (NASR_RB_DBG): 1 = epilogue drains without math/stores, 2 = no MMAs, 4 = no zeroing, 8 = timeline stamps, 16 = no global stores
 };
@@ -82,6 +83,7 @@ void ring_pack_weights(int arch, int grp, int k, const float* conv_w, const floa
                        float* inv_sw, float* inv_sr);
 cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s);
 int ring_debug_stamps(unsigned long long* host, int max_ctas);
+int ring_debug_steps(unsigned long long* host);
 cudaError_t ring_plan(int arch, int sm_count, long long cached_n, RingArgs& a, long long* grid_out);
 int ring_debug_plan(int arch, int k, int d, int B, long long T, long long in_row0, int sm_count, long long* out16);
 

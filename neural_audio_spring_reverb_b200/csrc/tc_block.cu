@@ -169,6 +169,7 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+    prof_stamp(a.prof, 0);
     for (int i = 0; i < TC_MAX_R; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], TC_NW); }
     for (int i = 0; i < NCS; ++i) mbar_init(&cfull[i], 1);
     mbar_init(wfull, 1);
@@ -457,6 +458,7 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) prof_stamp(a.prof, 1);
   if (warp == TC_PRODUCER_WARP) tmem_dealloc(tmem, 512);
 }
 

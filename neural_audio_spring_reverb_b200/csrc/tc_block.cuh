@@ -32,6 +32,7 @@ struct TcArgs {
   const float* wout;    // [out_ch][32]
   int out_ch, final_tanh;
   unsigned int* sat_flag;   // set when a SPLIT16 output had to be clamped to +-65504
+  unsigned long long* prof;   // nasr_forward_profiled: {start, end} stamps of this launch, or NULL
   int dbg;           // dev only (NASR_TC_DBG): 1 = issue no MMAs, 2 = epilogue skips math + stores
 };
 

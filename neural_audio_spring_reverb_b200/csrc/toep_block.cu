@@ -101,6 +101,7 @@ toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
   constexpr int MMA_WARP = 0;   // lane 0 of builder warp 0 doubles as the MMA issuer
 
   if (threadIdx.x == 0) {
+    prof_stamp(a.prof, 0);
     for (int i = 0; i < TP_STAGES; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < TP_SLOTS; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
     mbar_init(wfull, 1);
@@ -436,6 +437,7 @@ toep_first_kernel(const __grid_constant__ CUtensorMap w_map, const ToepArgs a) {
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) prof_stamp(a.prof, 1);
   if (warp == MMA_WARP) tmem_dealloc(tmem, 512);
 }
 

@@ -22,6 +22,7 @@ struct ToepArgs {
   int ld_affine;
   float slope, inv_sw, inv_sr;
   unsigned int* sat_flag;
+  unsigned long long* prof;    // nasr_forward_profiled: {start, end} stamps of this launch, or NULL
   unsigned long long* dbg_buf; // dev only: per-tile timeline stamps of CTA 0
   int dbg;                     // dev only (NASR_TOEP_DBG): 1 = epilogue only drains TMEM, 2 = builders skip the tile build
 };

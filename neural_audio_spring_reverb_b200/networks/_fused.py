@@ -12,6 +12,14 @@ from torch import Tensor
 from .. import _native
 
 
+def _async_device_forward() -> bool:
+    """NASR_ASYNC=1: `model(x_cuda)` only enqueues (no stream sync, no range check); the caller polls
+    `model.saturated()`.  Default: the call waits for its result and silently redoes it on the fp32 kernels when an
+    activation left the fp16 range of the tensor-core path - the reference forward has no input-range limit
+    (tcn.py:150-155), so neither has the drop-in."""
+    return os.environ.get("NASR_ASYNC", "0").lower() not in ("0", "", "false", "no")
+
+
 def _path_from_env() -> int:
     v = os.environ.get("NASR_PATH", "auto").lower()
     if v in ("auto", "0", ""):
@@ -175,8 +183,11 @@ class FusedNetMixin:
             if T > 0:
                 if chunk:
                     eng.forward_chunk(xc.data_ptr(), y.data_ptr(), B, T, stream)
-                else:
+                elif self.__dict__.get("_nasr_async", None) or (self.__dict__.get("_nasr_async", None) is None
+                                                                and _async_device_forward()):
                     eng.forward(xc.data_ptr(), y.data_ptr(), B, T, stream)
+                else:
+                    eng.forward_checked(xc.data_ptr(), y.data_ptr(), B, T, stream)
             return y
         # host tensors: the engine copies in, runs, copies out (e2e path of make_inference)
         xc = x if (x.dtype == torch.float32 and x.is_contiguous() and not x.requires_grad) \
@@ -196,10 +207,16 @@ class FusedNetMixin:
         eng.forward_host(xc.data_ptr(), cptr, y.data_ptr(), B, T, stream)
         return y
 
+    def set_async(self, flag: Optional[bool]) -> None:
+        """True: device-tensor forwards only enqueue work (poll `saturated()` yourself); False: every forward checks
+        the fp16-range flag and falls back to the fp32 kernels by itself; None: follow NASR_ASYNC (default: checked)."""
+        self.__dict__["_nasr_async"] = flag
+
     def saturated(self) -> bool:
-        """True if the last device-tensor forward had to clamp an activation to the fp16 range of
-        the tensor-core path (|a| > 65504): its result is then not trustworthy - run with
-        NASR_PATH=fp32. (Host-tensor forwards detect this themselves and fall back.) Synchronises."""
+        """True if the last forward had to clamp an activation to the fp16 range of the tensor-core path
+        (|a| * 64 > 65504).  Checked forwards (the default, and every host-tensor forward) have then already been
+        redone on the fp32 kernels; after an asynchronous forward (`set_async(True)` / NASR_ASYNC=1, or a streaming
+        chunk) the result is not trustworthy - run with NASR_PATH=fp32.  Synchronises."""
         eng = self._engine()
         dev = torch.device("cuda", eng.device)
         return eng.saturated(torch.cuda.current_stream(dev).cuda_stream)
@@ -215,7 +232,8 @@ class FusedNetMixin:
     def forward_chunk(self, x: Tensor, cond: Optional[Tensor] = None) -> Tensor:
         """Process the next chunk of a stream; history of the last (k-1)*d input
         samples of every block is carried across calls."""
-        if self.__dict__.get("_nasr_stream_B") != x.shape[0] or self.__dict__.get("_nasr_cache") is None:
+        self._engine()   # may rebuild (parameters changed in place) and then forgets the stream: decide afterwards
+        if self.__dict__.get("_nasr_stream_B") != x.shape[0]:
             self.reset_stream(x.shape[0])
         return self._nasr_run(x, cond, True)
 

@@ -216,9 +216,9 @@ def test_postprocess_on_device_matches_fp64_oracle(rows, T, sr):
 
 
 def test_fp16_range_guard_falls_back_to_fp32_kernels():
-    """Activations beyond +-65504 do not fit the SPLIT16 planes of the tensor-core path: the
-    host-tensor forward detects the clamp and redoes the call on the fp32 kernels; the
-    device-tensor forward reports it through saturated()."""
+    """Activations beyond +-65504 do not fit the SPLIT16 planes of the tensor-core path.  The reference forward has
+    no input-range limit (tcn.py:150-155), so by default BOTH the host-tensor and the device-tensor forward detect the
+    clamp and redo the call on the fp32 kernels; only the explicitly asynchronous mode leaves it to saturated()."""
     cfg = O.CONFIGS["cfg2"]
     sd = O.config_state("cfg2")
     m = build_model(cfg, sd, DEV)
@@ -227,10 +227,80 @@ def test_fp16_range_guard_falls_back_to_fp32_kernels():
     ref = O.forward(sd, O.config_dilations(cfg), x, cond)
     y_host = m(x, cond)                                # host path: automatic fallback
     assert rel_err(y_host, ref) <= REL_TOL
-    y_dev = m(x.to(DEV), cond.to(DEV))                 # device path: flagged, not silently wrong
-    assert m.saturated() is True
+    n0 = m._engine().sat_fallbacks()
+    y_dev = m(x.to(DEV), cond.to(DEV))                 # device path: automatic fallback as well
+    assert rel_err(y_dev, ref) <= REL_TOL
+    assert m._engine().sat_fallbacks() == n0 + 1 and m.saturated() is True
     small = m(O.make_input(1, 1, 20000).to(DEV), cond.to(DEV))
-    assert m.saturated() is False and torch.isfinite(small).all() and torch.isfinite(y_dev).all()
+    assert m.saturated() is False and m._engine().sat_fallbacks() == n0 + 1 and torch.isfinite(small).all()
+    m.set_async(True)                                  # opt-out: enqueue only, the caller polls the flag
+    y_async = m(x.to(DEV), cond.to(DEV))
+    assert m.saturated() is True and torch.isfinite(y_async).all() and m._engine().sat_fallbacks() == n0 + 1
+    m.set_async(None)
+
+
+def test_back_to_back_host_forwards_with_alternating_cond():
+    """Programmatic dependent launch: block 1's CTAs may become resident while the fold kernel of the same call still
+    writes scale / shift (short clips leave SMs free).  Alternate the conditioning on queued small-T host forwards: every
+    result must use ITS cond (the epilogue warps now wait on griddepcontrol before reading the tables)."""
+    cfg = O.CONFIGS["cfg2"]
+    sd = O.config_state("cfg2")
+    m = build_model(cfg, sd, DEV)
+    dil = O.config_dilations(cfg)
+    conds = [torch.tensor([[0.0, 1.0]]), torch.tensor([[1.0, 0.0]]), torch.tensor([[0.3, 0.9]])]
+    for T in (700, 4096, 15000):
+        x = O.make_input(1, 1, T)
+        refs = [O.forward(sd, dil, x, c) for c in conds]
+        assert rel_err(refs[0], refs[1]) > 1e-2                      # the conds really change the output
+        for rep in range(12):
+            j = rep % len(conds)
+            assert rel_err(m(x, conds[j]), refs[j]) <= REL_TOL, (T, rep)
+        xd = x.to(DEV)
+        m.set_async(True)
+        ys = [m(xd, conds[rep % len(conds)].to(DEV)) for rep in range(12)]   # queued without any host sync
+        m.set_async(None)
+        for rep, y in enumerate(ys):
+            assert rel_err(y, refs[rep % len(conds)]) <= REL_TOL, (T, rep)
+
+
+def test_cfg4_shard_full_length_clips_against_cpu():
+    """BASELINE config 4: one GPU's shard of the 512-clip batch = 64 clips x 10 s.  SURVEY 8(d): parity on >= 8 clips
+    (first / last of the shard and six inside) at FULL length against the CPU oracle; the shard runs as one call."""
+    cfg = O.CONFIGS["cfg2"]
+    sd = O.config_state("cfg2")
+    m = build_model(cfg, sd, DEV)
+    dil = O.config_dilations(cfg)
+    B, T = 64, 480000
+    g = torch.Generator(device=DEV).manual_seed(4)
+    x = torch.rand((B, 1, T), device=DEV, generator=g) * 2 - 1
+    x *= torch.linspace(0.05, 1.0, B, device=DEV).view(B, 1, 1)      # clips at different levels
+    cond = torch.rand((B, 2), device=DEV, generator=g)               # and different knob settings
+    y = m(x, cond)
+    assert m.saturated() is False
+    paths = [m._engine().block_path(i) for i in range(cfg["n_blocks"])]
+    assert all(p == 2 for p in paths[1:]), paths
+    worst = 0.0
+    for b in (0, 1, 17, 31, 32, 46, 62, 63):
+        ref = O.forward(sd, dil, x[b:b + 1].cpu(), cond[b:b + 1].cpu())
+        worst = max(worst, rel_err(y[b:b + 1], ref))
+    assert worst <= REL_TOL, worst
+    # the same clips alone (B = 1 launch plan) agree with their rows of the batch
+    for b in (0, 63):
+        assert rel_err(m(x[b:b + 1], cond[b:b + 1]), y[b:b + 1]) <= 1e-6
+
+
+def test_cfg3_full_length_cond_sweep_against_cpu():
+    """BASELINE config 3 at its real size: GCN 10 x 32, k = 15, one 10 s clip, the five knob settings."""
+    cfg = O.CONFIGS["cfg3"]
+    sd = O.config_state("cfg3")
+    m = build_model(cfg, sd, DEV)
+    dil = O.config_dilations(cfg)
+    x = O.make_input(1, 1, 480000)
+    xd = x.to(DEV)
+    for c in (0.0, 0.25, 0.5, 0.75, 1.0):
+        cond = torch.tensor([[c, c]])
+        ref = O.forward(sd, dil, x, cond)
+        assert rel_err(m(xd, cond.to(DEV)), ref) <= REL_TOL, c
 
 
 @pytest.mark.parametrize("cname", ["cfg2", "cfg3", "tcn-shipped"])

@@ -18,4 +18,13 @@ eng = m._engine(); yd = torch.empty_like(y); best = None
 for _ in range(5):
     ms = eng.forward_profiled(x.data_ptr(), yd.data_ptr(), B, T)
     best = ms if best is None else [min(a, b) for a, b in zip(best, ms)]
+m.set_async(True)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(30)]
+for _ in range(5): m(x, c)
+for s_, e_ in ev:
+    flush.zero_(); s_.record(); m(x, c); e_.record()
+torch.cuda.synchronize()
+tt = sorted(s_.elapsed_time(e_) for s_, e_ in ev)
+print(f"  forward (events, L2 flushed): median {tt[len(tt)//2]*1e3:.1f} us, min {tt[0]*1e3:.1f} us -> {B*T/tt[len(tt)//2]/1e6:.3f} G samples/s; sum(blocks) {sum(best)*1e3:.1f} us")
 print(f"{cname} B={B} T={T} dbg={os.environ.get('NASR_RB_DBG')} lib={os.path.basename(os.environ.get('NASR_LIB','default'))} blocks(us)={[round(v*1e3,1) for v in best]}", flush=True)

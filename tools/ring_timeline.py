@@ -28,3 +28,16 @@ print("dbg", os.environ["NASR_RB_DBG"], "B", B, "CTAs", len(a), "(times in us re
 for i, nm in enumerate(names):
     col = (a[:, i] - t0) / 1e3
     print(f"{nm:12s} min {col.min():8.2f}  median {np.median(col):8.2f}  max {col.max():8.2f}")
+
+sbuf = (ctypes.c_ulonglong * 256)()
+lib.nasr_debug_ring_steps(sbuf)
+st = np.frombuffer(sbuf, dtype=np.uint64).reshape(4, 64).astype(np.int64)
+base = a[0, 0]
+print("CTA 0 per step (us since its entry): tile requested | MMAs issued (d = delta to previous step) | epilogue drained | rows handed off")
+prev = None
+for q in range(64):
+    if st[0, q] == 0 and st[3, q] == 0: continue
+    f = lambda v: f"{(v - base) / 1e3:7.2f}" if v else "      -"
+    d = f"{(st[0, q] - prev) / 1e3:5.2f}" if prev and st[0, q] else "    -"
+    print(f"step {q - 14:3d}: {f(st[3, q])} | {f(st[0, q])} (d {d}) | {f(st[1, q])} | {f(st[2, q])}")
+    if st[0, q]: prev = st[0, q]
