@@ -4,10 +4,18 @@
     python bench.py --gpus N --steps K --warmup W            # our CUDA engine
     python bench.py --impl reference --gpus N --steps K ...   # CPU arm (oracle port of the reference forward)
 
-A "step" is one forward of the workload: BASELINE.json configs[1] (cfg2: TCN 10 blocks,
-32 ch, k = 15, dilations 2**i, one 10 s clip @ 48 kHz mono) per GPU; with --gpus N every
-rank runs its own shard of clips (weak scaling, no data-path collective; NCCL only
-broadcasts the weight blob once).  Prints ONE JSON line on rank 0.
+The contract line (`value`, `e2e`, `roofline`, `cpu_baseline`, `clocks`) is measured on BASELINE.json configs[1]
+(cfg2: TCN 10 blocks, 32 ch, k = 15, dilations 2**i, ONE 10 s clip @ 48 kHz mono per GPU); with --gpus N every rank
+runs its own clip (weak scaling, no data-path collective; NCCL only broadcasts the weight blob once).  The other
+BASELINE configs ride in the same JSON line as sub-records under "configs":
+
+    cfg3  GCN 10 x 32, k = 15, one 10 s clip, the five knob settings (parity of each against the CPU port)
+    cfg4  cfg2's network, 64 clips x 10 s per GPU (512 clips at N = 8): device-resident, end to end, parity of >= 8
+          full-length clips (first / last of the shards of ranks 0 and N-1 and more inside)
+    cfg5  cfg2's network as a stream: 60 min of audio in 65 536-sample chunks and 5 min in 1 024-sample chunks
+          (Neutone buffer), per-block history carried on the device; parity of the first 30 s against the CPU port
+
+Prints ONE JSON line on rank 0.  Anything under oracle/ is used only as the checker / CPU baseline.
 """
 import argparse
 import json
@@ -25,21 +33,34 @@ sys.path.insert(0, str(ROOT))
 import torch  # noqa: E402
 
 SR = 48000
+METRIC = "audio samples/sec (48 kHz mono)"
+DTYPE = "f32 (3 x fp16 split products on tcgen05, fp32 accumulate; fp32 in / out)"
 WORKLOADS = {
     # name: (arch, ctor kwargs, seconds)
     "cfg2": ("TCN", dict(n_channels=32, n_layers=10, dilation_growth=2, kernel_size=15, cond_dim=2), 10.0),
     "cfg3": ("GCN", dict(n_blocks=10, n_channels=32, dilation_growth=2, kernel_size=15, cond_dim=2), 10.0),
     "cfg1": ("TCN", dict(n_channels=16, n_layers=4, dilation_growth=2, kernel_size=3, cond_dim=2), 1.0),
 }
+CFG3_KNOBS = (0.0, 0.25, 0.5, 0.75, 1.0)
 
 
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]), bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]),
+                    bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
                     source="measured (MEASURED_PEAKS.json)")
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def base_config(workload, world, clips_per_gpu):
+    """The `config` dict of the contract line: identical for our arm and the reference arm."""
+    arch, kw, seconds = WORKLOADS[workload]
+    return dict(workload=workload, arch=arch, **kw, clip_seconds=seconds, clips_per_gpu=clips_per_gpu,
+                global_clips=world * clips_per_gpu, sample_rate=SR,
+                l2="flushed between timed iterations (256 MiB write)",
+                parallelism=f"clips sharded over {world} GPU(s), NCCL weight broadcast only")
 
 
 def randomise_state(model, seed=0):
@@ -87,7 +108,7 @@ def per_sample_costs(arch, kw):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons while the GPU runs the workload (B200_PROFILING.md)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -98,7 +119,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("NASR_SMI_MS", "50")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -109,41 +130,42 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self, t_begin=None, t_end=None, timed=None):
-        """Median SM clock over the samples taken while the GPU ran this workload
-        (t_begin..t_end); `timed` = (start, end) of the K timed steps, reported separately."""
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def window(self, t_begin, t_end, note):
+        """Median SM clock / reasons over the samples taken in [t_begin, t_end] (perf_counter seconds)."""
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        in_timed = 0
-        for ts, r in self.rows:
-            if (t_begin is not None and ts < t_begin) or (t_end is not None and ts > t_end):
+        for ts, r in list(self.rows):
+            if ts < t_begin or ts > t_end:
                 continue
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
+                power.append(float(r[2]))
                 for nme, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
-                if timed and timed[0] <= ts <= timed[1]:
-                    in_timed += 1
             except Exception:
                 continue
         return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
-                    samples=len(sm), samples_in_timed_steps=in_timed,
-                    window="warm-up + timed steps + the same forward looped for >= 1.5 s (nvidia-smi -lms 50)")
+                    power_w_max=max(power) if power else None, samples=len(sm), window=note)
 
 
+# ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_reference_arm(args):
     """The reference's CPU forward (oracle port on the same ATen CPU operators), all host threads."""
     from oracle import nasr_oracle as O
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     model, arch, kw, T = build_model(args.workload)
@@ -170,19 +192,314 @@ def cpu_reference_arm(args):
         t0 = time.perf_counter()
         O.forward(sd, model.dilations, x, cond)
         times.append(time.perf_counter() - t0)
-    best = min(times)
-    value = Ts / best
-    line = dict(impl="reference", metric="audio samples/sec (48 kHz mono)", value=value, unit="samples/s",
-                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * statistics.mean(times),
+    mean = statistics.mean(times)
+    value = Ts / mean          # mean of K, like the GPU arm (best of K is reported beside it)
+    line = dict(impl="reference", metric=METRIC, value=value, unit="samples/s",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * mean,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=args.workload, arch=arch, **kw, clip_seconds=Ts / SR, clips=1,
-                            note="reference forward restated on ATen CPU ops (oracle port); one clip, best of K"),
-                cpu_baseline=dict(value=value, unit="samples/s", cores=cores, kind="port",
-                                  sample=f"1 clip x {Ts / SR:.1f} s, fp32, {cores} threads, best of {args.steps}"),
+                config=base_config(args.workload, max(world, args.gpus), args.clips_per_gpu),
+                note=f"reference forward restated on ATen CPU ops (oracle port); one {Ts / SR:.1f} s clip of the workload per "
+                     "step on all host cores, mean of K (the forward is an FIR: samples/s does not depend on the clip length)",
+                cpu_baseline=dict(value=value, best_of_k=Ts / min(times), unit="samples/s", cores=cores, kind="port",
+                                  sample=f"1 clip x {Ts / SR:.1f} s, fp32, {cores} threads, mean of {args.steps}"),
                 e2e=dict(value=value, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ GPU arm helpers
+class Ctx:
+    pass
+
+
+def barrier(ctx):
+    if ctx.world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize(ctx.dev)
+
+
+def max_over_ranks(ctx, v):
+    if ctx.world == 1:
+        return float(v)
+    import torch.distributed as dist
+    t = torch.tensor([float(v)], device=ctx.dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+def time_device(ctx, model, x, cond, steps, warmup):
+    """Device-resident timing: K forwards, each bracketed by CUDA events on the launch stream, L2 flushed in between;
+    the device path runs in its asynchronous mode (enqueue only), the fp16-range flag is polled once afterwards.
+    Returns (sum of step ms = max over ranks, launches of this rank)."""
+    model.set_async(True)
+    eng = model._engine()
+    for _ in range(warmup):
+        model(x, cond)
+    barrier(ctx)
+    l0 = eng.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier(ctx)
+    t0 = time.perf_counter()
+    for s, e in ev:
+        ctx.flush.zero_()                      # L2 flush between timed iterations
+        s.record()
+        model(x, cond)
+        e.record()
+    barrier(ctx)
+    t1 = time.perf_counter()
+    launches = eng.launch_count() - l0
+    if model.saturated():
+        raise RuntimeError("an activation left the fp16 range during the timed region: the timing is void")
+    model.set_async(None)
+    total_ms = max_over_ranks(ctx, sum(s.elapsed_time(e) for s, e in ev))
+    return total_ms, launches, (t0, t1)
+
+
+def time_e2e(ctx, model, x_host, cond_host, n):
+    """End to end through the public API with HOST tensors: every call copies x in, runs, and returns the result in
+    pinned host memory (synchronous).  Returns seconds (max over ranks)."""
+    y = None
+    for _ in range(4):                       # keeps the previous result alive like the timed loop: both pinned blocks get cached
+        y = model(x_host, cond_host)
+    barrier(ctx)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        y = model(x_host, cond_host)
+    torch.cuda.synchronize(ctx.dev)
+    return max_over_ranks(ctx, time.perf_counter() - t0), y
+
+
+def profile_blocks(ctx, model, x, cond, reps=5):
+    """Per-block device time in the forward's own pipelined mode (kernel-side %globaltimer stamps, see
+    nasr_forward_profiled): block_ms[i] = end_i - end_{i-1}, so the figures add up to the forward's duration."""
+    eng = model._engine()
+    B, _, T = x.shape
+    yb = torch.empty((B, model.out_ch, T), device=ctx.dev)
+    stream = torch.cuda.current_stream(ctx.dev).cuda_stream
+    eng.set_cond(cond.data_ptr(), B, stream)
+    acc = None
+    for _ in range(reps):
+        ctx.flush.zero_()
+        ms = eng.forward_profiled(x.data_ptr(), yb.data_ptr(), B, T, stream)
+        acc = ms if acc is None else [a + b for a, b in zip(acc, ms)]
+    n = len(acc)
+    return [a / reps for a in acc], [eng.block_path(i) for i in range(n)]
+
+
+def roofline_of(arch, kw, B, T, block_ms, paths, traffic_key=None):
+    """Roofline of the dominant kernel = the mid-network block kernel (blocks 1 .. n-1 share it): ALGORITHMIC bytes and
+    FLOPs over its average pipelined launch time against the measured peaks.  `frac` is the larger of the
+    two algorithmic fractions; the fp16 FLOPs the tensor pipe really executes (3 per algorithmic one) stay beside it."""
+    pk = peaks()
+    costs = per_sample_costs(arch, kw)
+    n = len(block_ms)
+    mid = list(range(1, n)) if n > 1 else [0]
+    dom_ms = sum(block_ms[i] for i in mid) / len(mid)
+    dom_bytes = sum(costs[i]["bytes"] for i in mid) / len(mid) * B * T
+    dom_flops = sum(costs[i]["flops"] for i in mid) / len(mid) * B * T
+    gbs = dom_bytes / (dom_ms * 1e-3) / 1e9
+    tfs = dom_flops / (dom_ms * 1e-3) / 1e12
+    tensor_path = all(paths[i] in (1, 2) for i in mid)
+    ring_path = sum(1 for i in mid if paths[i] == 2) * 2 > len(mid)
+    hbm_frac = gbs / pk["hbm"]
+    # ONE tensor denominator: the sustained bf16 / fp16 figure of MEASURED_PEAKS.json (these launches sit inside a long,
+    # power-capped sequence of back-to-back kernels)
+    tensor_frac = tfs / pk["bf16_sustained"]
+    if hbm_frac >= tensor_frac or not tensor_path:
+        roof = dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=hbm_frac)
+    else:
+        roof = dict(bound="tensor", achieved=tfs, peak=pk["bf16_sustained"], unit="TFLOP/s", frac=tensor_frac)
+    kernel = ("ring_block_kernel" if ring_path else "tc_block_kernel") if tensor_path else "generic_block_kernel (fp32 FFMA)"
+    roof.update(traffic=None, kernel=kernel, peak_source=pk["source"] + "; tensor = sustained bf16 figure",
+                algorithmic_bytes_per_launch=dom_bytes, algorithmic_flops_per_launch=dom_flops, launch_ms=dom_ms,
+                hbm_gbs=gbs, hbm_frac=hbm_frac, algorithmic_tflops=tfs, tensor_frac_algorithmic=tensor_frac,
+                issued_fp16_tflops=3.0 * tfs if tensor_path else None,
+                issued_fp16_frac_of_sustained_peak=3.0 * tfs / pk["bf16_sustained"] if tensor_path else None,
+                fp32_ffma_frac_of_75tf=tfs / 75.0,
+                block_ms=block_ms, block_paths=paths, sum_block_ms=sum(block_ms),
+                timing="kernel-side %globaltimer stamps in the forward's own pipelined (PDL) mode; "
+                       "block_ms[i] = end_i - end_(i-1), first block from its own start",
+                whole_net_hbm_gbs=sum(c["bytes"] for c in costs) * B * T / (sum(block_ms) * 1e-3) / 1e9)
+    tpath = ROOT / "profiles" / "traffic.json"
+    if tpath.exists():
+        try:
+            tj = json.loads(tpath.read_text())
+            key = traffic_key or kernel.split(" ")[0]
+            roof["traffic"] = tj.get(key)
+            roof["traffic_note"] = tj.get("_note")
+        except Exception:
+            pass
+    return roof
+
+
+def cpu_check(model, x_host, cond_host, got, cores, repeats=0):
+    """CPU port of the reference forward on the same inputs: parity of `got` (and its timing when repeats > 0)."""
+    from oracle import nasr_oracle as O
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    torch.set_num_threads(cores)
+    secs = O.time_forward(sd, model.dilations, x_host, cond_host, repeats=repeats, threads=cores) if repeats else None
+    ref = O.forward(sd, model.dilations, x_host, cond_host)
+    g = got.detach().cpu().double()
+    r = ref.double()
+    err = float(((g - r).abs().flatten(1).max(1).values / r.abs().flatten(1).max(1).values.clamp_min(1e-30)).max())
+    return err, secs
+
+
+# ------------------------------------------------------------------------------------------------ sub-records
+def run_cfg3(ctx, args):
+    """GCN + FiLM conditioning sweep: one 10 s clip, five knob settings."""
+    model, arch, kw, T = build_model("cfg3")
+    model = model.to(ctx.dev).eval()
+    g = torch.Generator(device=ctx.dev).manual_seed(300 + ctx.rank)
+    x = torch.rand((1, 1, T), device=ctx.dev, generator=g) * 2 - 1
+    conds = [torch.full((1, 2), c, device=ctx.dev) for c in CFG3_KNOBS]
+    steps = max(5, min(args.steps, 40))
+    t_sec0 = time.perf_counter()
+    per_knob = []
+    total_ms = 0.0
+    launches = 0
+    for c in conds:
+        ms, l, _ = time_device(ctx, model, x, c, steps, 3)
+        per_knob.append(T * steps / (ms * 1e-3))
+        total_ms += ms
+        launches += l
+    value = ctx.world * T * steps * len(conds) / (total_ms * 1e-3)
+    x_host = x.cpu().pin_memory()
+    e2e_s, _ = time_e2e(ctx, model, x_host, conds[2].cpu().pin_memory(), 20)
+    rec = dict(workload="cfg3: GCN 10 x 32, k = 15, dilations 2**i, one 10 s clip, 5 knob settings (c0 = c1)",
+               samples_per_s=value, ms_per_clip=total_ms / (steps * len(conds)), steps_per_knob=steps,
+               samples_per_s_per_knob=dict(zip(map(str, CFG3_KNOBS), per_knob)), replicas=ctx.world,
+               e2e_samples_per_s=ctx.world * T * 20 / e2e_s, gpu_launches=launches)
+    if ctx.rank == 0:
+        block_ms, paths = profile_blocks(ctx, model, x, conds[2])
+        rec["roofline"] = roofline_of(arch, kw, 1, T, block_ms, paths, "ring_block_kernel<gcn>")
+        if not args.no_cpu_baseline:
+            errs = {}
+            secs = None
+            for c, cd in zip(CFG3_KNOBS, conds):
+                got = model(x, cd)
+                err, s = cpu_check(model, x.cpu(), cd.cpu(), got, ctx.cores, repeats=2 if c == 0.5 else 0)
+                errs[str(c)] = err
+                secs = s or secs
+            rec["cpu_baseline"] = dict(value=T / secs, unit="samples/s", cores=ctx.cores, kind="port",
+                                       sample="the same 10 s clip, knob 0.5, best of 2",
+                                       parity_rel_err_vs_gpu=errs, parity_tolerance=1e-4)
+        rec["clocks"] = ctx.sampler.window(t_sec0, time.perf_counter(), "cfg3 section")
+    return rec
+
+
+def run_cfg4(ctx, args):
+    """The batch: 64 clips x 10 s per GPU (BASELINE config 4 = 512 clips over 8 GPUs)."""
+    model, arch, kw, T = build_model("cfg2")
+    from neural_audio_spring_reverb_b200.distributed import broadcast_weights
+    broadcast_weights(model, src=0, device=ctx.dev)
+    model = model.to(ctx.dev).eval()
+    B = args.cfg4_clips
+    g = torch.Generator(device=ctx.dev).manual_seed(400 + ctx.rank)
+    x = torch.rand((B, 1, T), device=ctx.dev, generator=g) * 2 - 1
+    cond = torch.full((B, 2), 0.5, device=ctx.dev)
+    steps = max(3, min(args.steps, 10))
+    t_sec0 = time.perf_counter()
+    ms, launches, _ = time_device(ctx, model, x, cond, steps, 3)
+    value = ctx.world * B * T * steps / (ms * 1e-3)
+    x_host = x.cpu().pin_memory()
+    cond_host = cond.cpu().pin_memory()
+    n_e2e = 5
+    e2e_s, y_host = time_e2e(ctx, model, x_host, cond_host, n_e2e)
+    rec = dict(workload=f"cfg4: cfg2 network, {B} clips x 10 s per GPU, {ctx.world * B} clips over {ctx.world} GPU(s)",
+               samples_per_s=value, ms_per_step=ms / steps, steps=steps, clips_per_gpu=B, global_clips=ctx.world * B,
+               e2e=dict(value=ctx.world * B * T * n_e2e / e2e_s, unit="samples/s", steps=n_e2e,
+                        h2d_bytes_per_step=int(x_host.numel() * 4 + cond_host.numel() * 4),
+                        d2h_bytes_per_step=int(y_host.numel() * 4)),
+               gpu_launches=launches, scaling="weak")
+    # parity: clips {0, B-1} and two inside on ranks 0 and N-1 (N = 1: eight clips on rank 0), full length
+    check = []
+    if not args.no_cpu_baseline:
+        if ctx.world == 1:
+            check = sorted({0, 1, B // 4, B // 2 - 1, B // 2, 3 * B // 4, B - 2, B - 1})
+        elif ctx.rank in (0, ctx.world - 1):
+            check = sorted({0, B // 3, 2 * B // 3, B - 1})
+    worst = 0.0
+    if check:
+        y = model(x, cond)
+        for b in check:
+            err, _ = cpu_check(model, x[b:b + 1].cpu(), cond[b:b + 1].cpu(), y[b:b + 1], ctx.cores)
+            worst = max(worst, err)
+        del y
+    worst_all = max_over_ranks(ctx, worst)
+    if ctx.rank == 0:
+        block_ms, paths = profile_blocks(ctx, model, x, cond, reps=2)
+        rec["roofline"] = roofline_of(arch, kw, B, T, block_ms, paths, f"ring_block_kernel@B{B}")
+        if not args.no_cpu_baseline:
+            ranks = [0] if ctx.world == 1 else [0, ctx.world - 1]
+            per_rank = 8 if ctx.world == 1 else 4
+            rec["parity"] = dict(rel_err_max=worst_all, tolerance=1e-4, clips_checked=per_rank * len(ranks), ranks=ranks,
+                                 clips_of_each_rank=check, length="full 10 s", against="CPU port of the reference forward")
+        rec["clocks"] = ctx.sampler.window(t_sec0, time.perf_counter(), "cfg4 section")
+    del x, x_host, y_host
+    model.release_engine()
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_cfg5(ctx, args):
+    """Streaming: chunked causal inference with the per-block history carried across chunks on the device."""
+    model, arch, kw, _ = build_model("cfg2")
+    model = model.to(ctx.dev).eval()
+    cond = torch.full((1, 2), 0.5, device=ctx.dev)
+    rec = dict(workload="cfg5: cfg2 network as a stream, history of every block carried on the device", replicas=ctx.world)
+    t_sec0 = time.perf_counter()
+    g = torch.Generator(device=ctx.dev).manual_seed(500 + ctx.rank)
+    from neural_audio_spring_reverb_b200.streaming import CachedStream
+    for chunk, seconds in ((65536, args.cfg5_seconds), (1024, min(args.cfg5_seconds, 300.0))):
+        n_chunks = max(4, int(seconds * SR) // chunk)
+        total = n_chunks * chunk
+        x = torch.rand((1, 1, total), device=ctx.dev, generator=g) * 2 - 1
+        stream = CachedStream(model)
+        stream.reset(1)
+        for j in range(3):                               # warm-up chunks (also sizes the stream planes)
+            stream(x[:, :, j * chunk:(j + 1) * chunk], cond)
+        stream.reset(1)
+        eng = model._engine()
+        l0 = eng.launch_count()
+        barrier(ctx)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        keep = []
+        keep_n = (30 * SR + chunk - 1) // chunk if chunk == 65536 else 0     # first 30 s kept for the parity check
+        for j in range(n_chunks):
+            y = stream(x[:, :, j * chunk:(j + 1) * chunk], cond)
+            if j < keep_n:
+                keep.append(y)
+        ev1.record()
+        torch.cuda.synchronize(ctx.dev)
+        wall = time.perf_counter() - t0
+        dev_s = max_over_ranks(ctx, ev0.elapsed_time(ev1) * 1e-3)
+        wall = max_over_ranks(ctx, wall)
+        r = dict(chunk_samples=chunk, audio_seconds=total / SR, chunks=n_chunks,
+                 samples_per_s=ctx.world * total / dev_s, us_per_chunk=dev_s / n_chunks * 1e6,
+                 rtf=dev_s / (total / SR), wall_samples_per_s=ctx.world * total / wall,
+                 launches_per_chunk=(eng.launch_count() - l0) / n_chunks,
+                 saturated=bool(model.saturated()))
+        if keep and ctx.rank == 0 and not args.no_cpu_baseline:
+            got = torch.cat(keep, dim=2)
+            n30 = got.shape[2]
+            err, secs = cpu_check(model, x[:, :, :n30].cpu(), cond.cpu(), got, ctx.cores, repeats=1)
+            r["parity"] = dict(rel_err=err, tolerance=1e-4, seconds=n30 / SR,
+                               against="CPU port, one-shot forward over the first 30 s (chunked == one-shot in the reference)")
+            rec["cpu_baseline"] = dict(value=n30 / secs, unit="samples/s", cores=ctx.cores, kind="port",
+                                       sample=f"one-shot forward over the first {n30 / SR:.1f} s")
+        rec[f"chunk_{chunk}"] = r
+        del x, keep
+    if ctx.rank == 0:
+        rec["clocks"] = ctx.sampler.window(t_sec0, time.perf_counter(), "cfg5 section")
+    model.release_engine()
+    torch.cuda.empty_cache()
+    return rec
+
+
+# ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -191,6 +508,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--clips-per-gpu", type=int, default=1)
+    ap.add_argument("--configs", default="cfg3,cfg4,cfg5", help="sub-records to add to the line ('' = none)")
+    ap.add_argument("--cfg4-clips", type=int, default=64, help="clips per GPU of the cfg4 sub-record")
+    ap.add_argument("--cfg5-seconds", type=float, default=3600.0, help="stream length of the cfg5 sub-record")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="clip length of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -201,179 +521,125 @@ def main():
         return cpu_reference_arm(args)
 
     import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx = Ctx()
+    ctx.rank = int(os.environ.get("RANK", "0"))
+    ctx.world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU path)")
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
+    ctx.dev = torch.device("cuda", local)
+    ctx.cores = os.cpu_count() or 1
+    if ctx.world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=ctx.dev)
 
     from neural_audio_spring_reverb_b200.build import build_native
-    if rank == 0:
+    if ctx.rank == 0:
         build_native()
-    if world > 1:
+    if ctx.world > 1:
         dist.barrier()
+    from neural_audio_spring_reverb_b200 import hostaffinity
+    ctx.affinity = hostaffinity.pin_to_gpu(local, ctx.world)
 
     model, arch, kw, T = build_model(args.workload)
     # one-time weight broadcast over NCCL: every rank ends up with rank 0's blob
     from neural_audio_spring_reverb_b200.distributed import broadcast_weights
-    broadcast_weights(model, src=0, device=dev)
-    model = model.to(dev).eval()
+    broadcast_weights(model, src=0, device=ctx.dev)
+    model = model.to(ctx.dev).eval()
     eng = model._engine()
 
     B = args.clips_per_gpu
-    g = torch.Generator(device=dev).manual_seed(100 + rank)
-    x = torch.rand((B, 1, T), device=dev, generator=g) * 2 - 1
-    cond = torch.full((B, kw["cond_dim"]), 0.5, device=dev)
+    g = torch.Generator(device=ctx.dev).manual_seed(100 + ctx.rank)
+    x = torch.rand((B, 1, T), device=ctx.dev, generator=g) * 2 - 1
+    cond = torch.full((B, kw["cond_dim"]), 0.5, device=ctx.dev)
     x_host = x.cpu().pin_memory()
     cond_host = cond.cpu().pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    ctx.flush = torch.empty(256 << 20, dtype=torch.uint8, device=ctx.dev)   # > 126 MB L2
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    ctx.sampler = ClockSampler(local)
+    if ctx.rank == 0:
+        ctx.sampler.start()
 
     # ---- device-resident timing (value) ----
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    t_load0 = time.perf_counter()
-    for _ in range(args.warmup):
-        y = model(x, cond)
-    barrier()
-    l0 = eng.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_timed0 = time.perf_counter()
-    for s, e in ev:
-        flush.zero_()                      # L2 flush between timed iterations
-        s.record()
-        y = model(x, cond)
-        e.record()
-    barrier()
-    t_timed1 = time.perf_counter()
-    launches = eng.launch_count() - l0
-    # the timed region of this workload is milliseconds long - too short for nvidia-smi to see -
-    # so keep the identical forward running (untimed) until the sampler has a usable window
-    while time.perf_counter() - t_load0 < 1.5:
+    t_main0 = time.perf_counter()
+    total_ms, launches, timed = time_device(ctx, model, x, cond, args.steps, args.warmup)
+    value = ctx.world * B * T * args.steps / (total_ms * 1e-3)
+    # the same forward with the default (checked) device path: every call waits for its result and reads the fp16-range flag
+    chk_ms = 0.0
+    if ctx.rank == 0:
+        n_chk = min(args.steps, 50)
+        torch.cuda.synchronize(ctx.dev)
+        t0 = time.perf_counter()
+        for _ in range(n_chk):
+            model(x, cond)
+        torch.cuda.synchronize(ctx.dev)
+        chk_ms = (time.perf_counter() - t0) * 1e3 / n_chk
+    # the timed region of this workload is tens of milliseconds: keep the identical forward running (untimed) until the
+    # clock sampler has a usable window around it
+    model.set_async(True)
+    while time.perf_counter() - t_main0 < 1.5:
         for _ in range(8):
-            y = model(x, cond)
-        torch.cuda.synchronize(dev)
-    clocks = sampler.stop(t_load0, time.perf_counter(), (t_timed0, t_timed1)) if rank == 0 else None
-    step_ms = [s.elapsed_time(e) for s, e in ev]
-    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_s = float(total_ms) / 1e3
-    value = world * B * T * args.steps / total_s
+            model(x, cond)
+        torch.cuda.synchronize(ctx.dev)
+    model.set_async(None)
+    t_main1 = time.perf_counter()
 
     # ---- end to end through the public API with host buffers ----
     # every call is synchronous (H2D, forward, result written to the pinned output, stream sync); at least 50 calls so
     # that a single host hiccup (allocator, scheduler) does not decide a short run
     n_e2e = max(args.steps, 50)
-    for _ in range(5):
-        model(x_host, cond_host)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        y_host = model(x_host, cond_host)
-    torch.cuda.synchronize(dev)
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * T * n_e2e / float(e2e_s)
+    e2e_s, y_host = time_e2e(ctx, model, x_host, cond_host, n_e2e)
+    e2e_value = ctx.world * B * T * n_e2e / e2e_s
 
-    # ---- live per-kernel timing for the roofline (rank 0) ----
     line = None
-    if rank == 0:
-        yb = torch.empty_like(y)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        eng.set_cond(cond.data_ptr(), B, stream)
-        acc = None
-        reps = 5
-        for _ in range(reps):
-            flush.zero_()
-            ms = eng.forward_profiled(x.data_ptr(), yb.data_ptr(), B, T, stream)
-            acc = ms if acc is None else [a + b for a, b in zip(acc, ms)]
-        block_ms = [a / reps for a in acc]
-        costs = per_sample_costs(arch, kw)
-        pk = peaks()
-        n = len(block_ms)
-        paths = [eng.block_path(i) for i in range(n)]
-        # dominant kernel = the mid-network block kernel (blocks 1..n-1 share it); report its average launch
-        mid = list(range(1, n)) if n > 1 else [0]
-        dom_ms = sum(block_ms[i] for i in mid) / len(mid)
-        dom_bytes = sum(costs[i]["bytes"] for i in mid) / len(mid) * B * T
-        dom_flops = sum(costs[i]["flops"] for i in mid) / len(mid) * B * T
-        gbs = dom_bytes / (dom_ms * 1e-3) / 1e9
-        tfs = dom_flops / (dom_ms * 1e-3) / 1e12
-        tensor_path = all(paths[i] in (1, 2) for i in mid)
-        ring_path = sum(1 for i in mid if paths[i] == 2) * 2 > len(mid)
-        hbm_frac = gbs / pk["hbm"]
-        # The tcgen05 kernels compute an fp32-grade product as 3 fp16 products (xh*wh + xh*wl + xl*wh), so the
-        # tensor pipe executes 3x the algorithmic FLOPs; its roof for this work is measured fp16/bf16 peak / 3.
-        issued = 3.0 * tfs
-        # MEASURED_PEAKS.json carries a burst figure (kernel timed alone) and a sustained one (kernel inside a long,
-        # power-capped run).  The per-launch times above are taken right after hundreds of back-to-back forwards: when the
-        # SM clock sampled under that load sits well below its maximum, the sustained figure is the matching denominator.
-        sustained = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and
-                         clocks["sm_mhz"] < 0.9 * clocks["sm_max_mhz"])
-        bf16_peak = pk["bf16_sustained"] if sustained else pk["bf16"]
-        tensor_frac = issued / bf16_peak
-        if tensor_path and tensor_frac >= hbm_frac:
-            roof = dict(bound="tensor", achieved=issued, peak=bf16_peak, unit="TFLOP/s", frac=tensor_frac, traffic=None,
-                        note="achieved = fp16 tensor FLOPs executed (3 per algorithmic fp32-grade FLOP: split-fp16 "
-                             "product); algorithmic_tflops is the SURVEY 8d figure; hbm_* gives the HBM view of the same launch")
-        else:
-            roof = dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=hbm_frac, traffic=None)
-        roof.update(kernel=("ring_block_kernel" if ring_path else "tc_block_kernel") if tensor_path
-                    else "generic_block_kernel (fp32 FFMA)",
-                    peak_source=pk["source"] + (", sustained bf16 figure (SM clock under load %.0f of %.0f MHz)" % (clocks["sm_mhz"], clocks["sm_max_mhz"]) if sustained else ", burst bf16 figure"),
-                    frac_of_burst_peak=issued / pk["bf16"], launch_ms=dom_ms, hbm_gbs=gbs, hbm_frac=hbm_frac,
-                    algorithmic_tflops=tfs, issued_fp16_tflops=issued if tensor_path else None,
-                    fp32_ffma_frac_of_75tf=tfs / 75.0,
-                    block_ms=block_ms, block_paths=paths,
-                    whole_net_hbm_gbs=sum(c["bytes"] for c in costs) * B * T / (sum(block_ms) * 1e-3) / 1e9)
-        tpath = ROOT / "profiles" / "traffic.json"
-        if tpath.exists():
-            try:
-                roof["traffic"] = json.loads(tpath.read_text()).get(roof["kernel"].split(" ")[0])
-            except Exception:
-                pass
-
+    if ctx.rank == 0:
+        clocks = ctx.sampler.window(t_main0, t_main1, "warm-up + the K timed steps + the same forward looped to >= 1.5 s "
+                                    "(nvidia-smi -lms 50)")
+        clocks["samples_in_timed_steps"] = ctx.sampler.window(timed[0], timed[1], "")["samples"]
+        block_ms, paths = profile_blocks(ctx, model, x, cond)
+        roof = roofline_of(arch, kw, B, T, block_ms, paths)
         cpu = None
         if not args.no_cpu_baseline:
-            from oracle import nasr_oracle as O
-            cores = os.cpu_count() or 1
             Ts = min(T, int(args.cpu_seconds * SR))
-            sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
             xs = x_host[:1, :, :Ts].clone()
             cs = cond_host[:1].clone()
-            secs = O.time_forward(sd, model.dilations, xs, cs, repeats=3, threads=cores)
-            # the CPU forward doubles as a full-size parity check of this run
-            ref = O.forward(sd, model.dilations, xs, cs)
-            got = model(x[:1, :, :Ts], cond[:1]).cpu()
-            perr = float((got - ref).abs().max() / ref.abs().max())
-            cpu = dict(value=Ts / secs, unit="samples/s", cores=cores, kind="port",
-                       sample=f"1 clip x {Ts / SR:.1f} s of the same workload, fp32, {cores} threads, best of 3",
-                       parity_rel_err_vs_gpu=perr)
-
-        line = dict(metric="audio samples/sec (48 kHz mono)", value=value, unit="samples/s", n_gpus=world,
-                    steps=args.steps, warmup=args.warmup, ms_per_step=total_s * 1e3 / args.steps,
-                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=args.workload, arch=arch, **kw, clip_seconds=T / SR, clips_per_gpu=B,
-                                global_clips=world * B, sample_rate=SR, l2="flushed between timed iterations (256 MiB write)",
-                                parallelism=f"clips sharded over {world} GPU(s), NCCL weight broadcast only"),
-                    e2e=dict(value=e2e_value, unit="samples/s", steps=n_e2e, h2d_bytes_per_step=int(x_host.numel() * 4 + cond_host.numel() * 4),
+            got = model(x[:1, :, :Ts], cond[:1])
+            perr, secs = cpu_check(model, xs, cs, got, ctx.cores, repeats=3)   # doubles as a full-size parity check
+            cpu = dict(value=Ts / secs, unit="samples/s", cores=ctx.cores, kind="port",
+                       sample=f"1 clip x {Ts / SR:.1f} s of the same workload, fp32, {ctx.cores} threads, best of 3",
+                       parity_rel_err_vs_gpu=perr, parity_tolerance=1e-4)
+        line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=ctx.world,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=total_ms / args.steps,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype=DTYPE, data="synthetic",
+                    config=base_config(args.workload, ctx.world, B),
+                    device_path="asynchronous (set_async: enqueue only; fp16-range flag polled once after the timed region)",
+                    checked_device_path_ms_per_step=chk_ms,
+                    e2e=dict(value=e2e_value, unit="samples/s", steps=n_e2e,
+                             h2d_bytes_per_step=int(x_host.numel() * 4 + cond_host.numel() * 4),
                              d2h_bytes_per_step=int(y_host.numel() * 4)),
-                    gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu,
+                    host_affinity=ctx.affinity)
+    # ---- the other BASELINE configs ----
+    del x_host, y_host
+    model.release_engine()
+    subs = {}
+    want = [c for c in args.configs.split(",") if c]
+    runners = dict(cfg3=run_cfg3, cfg4=run_cfg4, cfg5=run_cfg5)
+    for name in want:
+        if name not in runners:
+            raise SystemExit(f"unknown sub-record {name!r}")
+        try:
+            subs[name] = runners[name](ctx, args)
+        except Exception as exc:   # a failing sub-record must not cost the contract line
+            subs[name] = dict(error=f"{type(exc).__name__}: {exc}")
+            if ctx.world > 1:
+                raise
+    ctx.sampler.stop()
+    if ctx.rank == 0:
+        line["configs"] = subs
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if ctx.world > 1:
         dist.barrier()
         dist.destroy_process_group()
 

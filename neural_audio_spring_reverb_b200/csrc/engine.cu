@@ -80,6 +80,11 @@ struct nasr_engine {
   DevBuf sfinal;   // streaming: channels-last output of the last block when out_net runs as its own kernel
   // host path
   DevBuf hx, hy, hc;
+  // pipelined host path (B >= 2): slices of the batch flow H2D -> forward -> D2H on three streams, double-buffered
+  cudaStream_t hs_in = nullptr, hs_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  DevBuf hx2[2], hy2[2];
+  bool host_pipe = true;   // NASR_HOST_PIPE=0: whole batch in one H2D / forward / D2H sequence (dev)
   size_t budget_bytes = (size_t)24 << 30;
   mutable std::string err;
   int64_t launches = 0;
@@ -327,6 +332,14 @@ void nasr_engine_destroy(nasr_engine* e) {
     release(e->plane[0]); release(e->plane[1]);
     for (auto& p : e->splane) release(p);
     release(e->scratch); release(e->sfinal); release(e->hx); release(e->hy); release(e->hc);
+    for (int q = 0; q < 2; ++q) {
+      release(e->hx2[q]); release(e->hy2[q]);
+      if (e->ev_in[q]) cudaEventDestroy(e->ev_in[q]);
+      if (e->ev_cmp[q]) cudaEventDestroy(e->ev_cmp[q]);
+      if (e->ev_out[q]) cudaEventDestroy(e->ev_out[q]);
+    }
+    if (e->hs_in) cudaStreamDestroy(e->hs_in);
+    if (e->hs_out) cudaStreamDestroy(e->hs_out);
   }
   delete e;
 }
@@ -373,6 +386,7 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
   e->ring_cache.resize(n);
   if (const char* env = getenv("NASR_PDL")) e->pdl = atoi(env) != 0;
   if (const char* env = getenv("NASR_ZEROCOPY")) e->zero_copy = atoi(env) != 0;
+  if (const char* env = getenv("NASR_HOST_PIPE")) e->host_pipe = atoi(env) != 0;
   const float* p = w;
   std::vector<FoldArgs> fold(n);
   int rc = NASR_OK;
@@ -611,6 +625,29 @@ static int forward_slice(nasr_engine* e, const float* x, float* y, int b0, int B
 static int forward_impl(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T, void* stream,
                         float* block_ms, bool tc = true);
 
+// activation planes for up to `want` clips of length T within the workspace budget; *slice = clips per pass
+static int ensure_planes(nasr_engine* e, int want, int64_t T, cudaStream_t s, int* slice) {
+  const size_t per_clip = (size_t)T * plane_row_bytes(e);
+  const int nplanes = planes_needed(e);
+  *slice = want;
+  if (nplanes > 0) {
+    const size_t fit = e->budget_bytes / (per_clip * nplanes);
+    if (fit < 1) {
+      // one clip does not fit the workspace budget: still try, cudaMalloc decides
+      *slice = 1;
+    } else if ((size_t)*slice > fit) {
+      *slice = (int)fit;
+    }
+    for (int q = 0; q < nplanes; ++q) {
+      if (e->plane[q].cap < per_clip * *slice + plane_slack_bytes()) {
+        NASR_CUDA(e, cudaStreamSynchronize(s));
+        NASR_CUDA(e, ensure(e->plane[q], per_clip * *slice + plane_slack_bytes()));
+      }
+    }
+  }
+  return NASR_OK;
+}
+
 int64_t nasr_sat_fallbacks(const nasr_engine* e) { return e ? e->sat_fallbacks : 0; }
 
 int nasr_forward(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t T, void* stream) {
@@ -665,24 +702,8 @@ static int forward_impl(nasr_engine* e, const float* x_dev, float* y_dev, int B,
     if (rc != NASR_OK) return rc;
   }
   const int n = (int)e->blocks.size();
-  const size_t per_clip = (size_t)T * plane_row_bytes(e);
-  const int nplanes = planes_needed(e);
   int slice = B;
-  if (nplanes > 0) {
-    const size_t fit = e->budget_bytes / (per_clip * nplanes);
-    if (fit < 1) {
-      // one clip does not fit the workspace budget: still try, cudaMalloc decides
-      slice = 1;
-    } else if ((size_t)slice > fit) {
-      slice = (int)fit;
-    }
-    for (int q = 0; q < nplanes; ++q) {
-      if (e->plane[q].cap < per_clip * slice + plane_slack_bytes()) {
-        NASR_CUDA(e, cudaStreamSynchronize(s));
-        NASR_CUDA(e, ensure(e->plane[q], per_clip * slice + plane_slack_bytes()));
-      }
-    }
-  }
+  if (int rcP = ensure_planes(e, B, T, s, &slice)) return rcP;
   sat_begin(e);   // this call's own flag word (earlier calls still in flight raise theirs)
   // Profiled mode: the forward runs exactly as always (same launches, programmatic dependent launch intact); every
   // kernel stamps %globaltimer at its earliest CTA start and latest CTA end.  block_ms[i] = end_i - end_{i-1} (block
@@ -722,16 +743,98 @@ static int forward_impl(nasr_engine* e, const float* x_dev, float* y_dev, int B,
   return rc;
 }
 
+// Batches of two or more clips: the clips are independent, so slices of the batch flow through H2D copy -> forward ->
+// D2H copy on three streams with double-buffered staging; in steady state the copies of the neighbouring slices hide
+// behind the kernels of the current one (inference.py:39,58,77 do the three steps back to back for the whole batch).
+static int forward_host_pipelined(nasr_engine* e, const float* x_host, const float* cond_host, float* y_host, int B,
+                                  int64_t T, cudaStream_t s) {
+  const int cd = e->desc.cond_dim;
+  if (!e->hs_in) {
+    NASR_CUDA(e, cudaStreamCreateWithFlags(&e->hs_in, cudaStreamNonBlocking));
+    NASR_CUDA(e, cudaStreamCreateWithFlags(&e->hs_out, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; ++q) {
+      NASR_CUDA(e, cudaEventCreateWithFlags(&e->ev_in[q], cudaEventDisableTiming));
+      NASR_CUDA(e, cudaEventCreateWithFlags(&e->ev_cmp[q], cudaEventDisableTiming));
+      NASR_CUDA(e, cudaEventCreateWithFlags(&e->ev_out[q], cudaEventDisableTiming));
+    }
+  }
+  // slice size: at least ~8 slices per call where the batch allows it, at most 8 clips (larger launches gain nothing)
+  int nb = B / 8;
+  if (nb < 1) nb = 1;
+  if (nb > 8) nb = 8;
+  int fit = nb;
+  if (int rcP = ensure_planes(e, nb, T, s, &fit)) return rcP;
+  if (fit < nb) nb = fit;
+  const size_t xs = (size_t)e->desc.in_ch * T, ys = (size_t)e->desc.out_ch * T;   // floats per clip
+  for (int q = 0; q < 2; ++q) {
+    if (e->hx2[q].cap < nb * xs * sizeof(float) || e->hy2[q].cap < nb * ys * sizeof(float)) {
+      NASR_CUDA(e, cudaDeviceSynchronize());
+      NASR_CUDA(e, ensure(e->hx2[q], nb * xs * sizeof(float)));
+      NASR_CUDA(e, ensure(e->hy2[q], nb * ys * sizeof(float)));
+    }
+  }
+  // cond: folded once for the whole batch on the compute stream
+  const float* cdev = nullptr;
+  const float* cinl = nullptr;
+  if (cd > 0 && cond_host) {
+    if ((size_t)B * cd <= NASR_COND_INLINE_MAX) {
+      cinl = cond_host;
+    } else {
+      NASR_CUDA(e, ensure(e->hc, (size_t)B * cd * sizeof(float)));
+      NASR_CUDA(e, cudaMemcpyAsync(e->hc.p, cond_host, (size_t)B * cd * sizeof(float), cudaMemcpyHostToDevice, s));
+      cdev = (const float*)e->hc.p;
+    }
+  }
+  int rc = set_cond_impl(e, cdev, cinl, B, (void*)s);
+  if (rc != NASR_OK) return rc;
+  sat_begin(e);
+  int it = 0;
+  for (int b0 = 0; b0 < B; b0 += nb, ++it) {
+    const int q = it & 1;
+    const int n = (B - b0 < nb) ? B - b0 : nb;
+    // staging buffer q was last read by the forward of slice it - 2 and its result last copied out by D2H it - 2
+    if (it >= 2) NASR_CUDA(e, cudaStreamWaitEvent(e->hs_in, e->ev_cmp[q], 0));
+    NASR_CUDA(e, cudaMemcpyAsync(e->hx2[q].p, x_host + (size_t)b0 * xs, n * xs * sizeof(float), cudaMemcpyHostToDevice, e->hs_in));
+    NASR_CUDA(e, cudaEventRecord(e->ev_in[q], e->hs_in));
+    NASR_CUDA(e, cudaStreamWaitEvent(s, e->ev_in[q], 0));
+    if (it >= 2) NASR_CUDA(e, cudaStreamWaitEvent(s, e->ev_out[q], 0));
+    rc = forward_slice(e, (const float*)e->hx2[q].p, (float*)e->hy2[q].p, b0, n, T, s, /*tc=*/true);
+    if (rc != NASR_OK) return rc;
+    NASR_CUDA(e, cudaEventRecord(e->ev_cmp[q], s));
+    NASR_CUDA(e, cudaStreamWaitEvent(e->hs_out, e->ev_cmp[q], 0));
+    NASR_CUDA(e, cudaMemcpyAsync(y_host + (size_t)b0 * ys, e->hy2[q].p, n * ys * sizeof(float), cudaMemcpyDeviceToHost, e->hs_out));
+    NASR_CUDA(e, cudaEventRecord(e->ev_out[q], e->hs_out));
+  }
+  NASR_CUDA(e, cudaStreamSynchronize(e->hs_out));
+  NASR_CUDA(e, cudaStreamSynchronize(s));
+  if (sat_word(e)) {
+    // an activation exceeded the fp16 range of the SPLIT16 planes: redo the whole call on the fp32 kernels
+    e->sat_fallbacks += 1;
+    const size_t xb = (size_t)B * xs * sizeof(float), yb = (size_t)B * ys * sizeof(float);
+    NASR_CUDA(e, ensure(e->hx, xb));
+    NASR_CUDA(e, ensure(e->hy, yb));
+    NASR_CUDA(e, cudaMemcpyAsync(e->hx.p, x_host, xb, cudaMemcpyHostToDevice, s));
+    rc = forward_impl(e, (const float*)e->hx.p, (float*)e->hy.p, B, T, (void*)s, nullptr, /*tc=*/false);
+    if (rc != NASR_OK) return rc;
+    NASR_CUDA(e, cudaMemcpyAsync(y_host, e->hy.p, yb, cudaMemcpyDeviceToHost, s));
+    NASR_CUDA(e, cudaStreamSynchronize(s));
+    sat_word(e) = 1;
+  }
+  return NASR_OK;
+}
+
 int nasr_forward_host(nasr_engine* e, const float* x_host, const float* cond_host, float* y_host, int B, int64_t T,
                       void* stream) {
   if (!e) return NASR_ERR_INVALID;
   if (!x_host || !y_host) return fail(e, NASR_ERR_INVALID, "x or y is NULL");
   if (B < 1 || T < 0) return fail(e, NASR_ERR_INVALID, "B must be >= 1 and T >= 0");
+  if (int rcB = check_clips(e, B)) return rcB;
   const int cd = e->desc.cond_dim;
   if (e->desc.has_film && cd > 0 && !cond_host) return fail(e, NASR_ERR_INVALID, "cond is NULL but cond_dim > 0");
   if (T == 0) return NASR_OK;
   DeviceGuard guard(e->device);
   cudaStream_t s = (cudaStream_t)stream;
+  if (B >= 2 && e->host_pipe) return forward_host_pipelined(e, x_host, cond_host, y_host, B, T, s);
   // dev: NASR_E2E_DBG=1 prints host-side and device-side phase times of this call to stderr
   static int dbg = -1;
   if (dbg < 0) { const char* env = getenv("NASR_E2E_DBG"); dbg = env ? atoi(env) : 0; }
