@@ -113,10 +113,15 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index, enabled=True):
+        self.rows, self.proc, self.index, self.enabled = [], None, index, enabled
 
     def start(self):
+        """(Re)start polling.  The sampler only runs around device-timed regions: nvidia-smi polling takes driver locks
+        and measurably slows the synchronous host-tensor calls of the end-to-end legs (0.89 vs 1.03 G samples/s at
+        -lms 20 on one GPU; with eight ranks on one host every rank feels rank 0's poller)."""
+        if not self.enabled or self.proc:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", os.environ.get("NASR_SMI_MS", "50")],
@@ -137,11 +142,12 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+            self.proc = None
 
     def window(self, t_begin, t_end, note):
         """Median SM clock / reasons over the samples taken in [t_begin, t_end] (perf_counter seconds)."""
-        if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        if not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no nvidia-smi sample in the window"], samples=0, window=note)
         sm, mx, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, r in list(self.rows):
@@ -255,6 +261,18 @@ def time_device(ctx, model, x, cond, steps, warmup):
     return total_ms, launches, (t0, t1)
 
 
+def keep_busy(ctx, model, x, cond, t_begin, seconds):
+    """Loop the same forward (untimed) until `seconds` have passed since t_begin, so that the clock sampler gets a
+    usable window around a timed region that is only milliseconds long.  Returns the end of the window."""
+    model.set_async(True)
+    while time.perf_counter() - t_begin < seconds:
+        for _ in range(4):
+            model(x, cond)
+        torch.cuda.synchronize(ctx.dev)
+    model.set_async(None)
+    return time.perf_counter()
+
+
 def time_e2e(ctx, model, x_host, cond_host, n):
     """End to end through the public API with HOST tensors: every call copies x in, runs, and returns the result in
     pinned host memory (synchronous).  Returns seconds (max over ranks)."""
@@ -354,6 +372,7 @@ def run_cfg3(ctx, args):
     x = torch.rand((1, 1, T), device=ctx.dev, generator=g) * 2 - 1
     conds = [torch.full((1, 2), c, device=ctx.dev) for c in CFG3_KNOBS]
     steps = max(5, min(args.steps, 40))
+    ctx.sampler.start()
     t_sec0 = time.perf_counter()
     per_knob = []
     total_ms = 0.0
@@ -363,6 +382,8 @@ def run_cfg3(ctx, args):
         per_knob.append(T * steps / (ms * 1e-3))
         total_ms += ms
         launches += l
+    t_sec1 = keep_busy(ctx, model, x, conds[2], t_sec0, 1.0)
+    ctx.sampler.stop()
     value = ctx.world * T * steps * len(conds) / (total_ms * 1e-3)
     x_host = x.cpu().pin_memory()
     e2e_s, _ = time_e2e(ctx, model, x_host, conds[2].cpu().pin_memory(), 20)
@@ -384,7 +405,7 @@ def run_cfg3(ctx, args):
             rec["cpu_baseline"] = dict(value=T / secs, unit="samples/s", cores=ctx.cores, kind="port",
                                        sample="the same 10 s clip, knob 0.5, best of 2",
                                        parity_rel_err_vs_gpu=errs, parity_tolerance=1e-4)
-        rec["clocks"] = ctx.sampler.window(t_sec0, time.perf_counter(), "cfg3 section")
+        rec["clocks"] = ctx.sampler.window(t_sec0, t_sec1, "cfg3: the timed forwards + the same forward looped to >= 1 s")
     return rec
 
 
@@ -399,8 +420,11 @@ def run_cfg4(ctx, args):
     x = torch.rand((B, 1, T), device=ctx.dev, generator=g) * 2 - 1
     cond = torch.full((B, 2), 0.5, device=ctx.dev)
     steps = max(3, min(args.steps, 10))
+    ctx.sampler.start()
     t_sec0 = time.perf_counter()
     ms, launches, _ = time_device(ctx, model, x, cond, steps, 3)
+    t_sec1 = keep_busy(ctx, model, x, cond, t_sec0, 1.0)
+    ctx.sampler.stop()
     value = ctx.world * B * T * steps / (ms * 1e-3)
     x_host = x.cpu().pin_memory()
     cond_host = cond.cpu().pin_memory()
@@ -435,7 +459,7 @@ def run_cfg4(ctx, args):
             per_rank = 8 if ctx.world == 1 else 4
             rec["parity"] = dict(rel_err_max=worst_all, tolerance=1e-4, clips_checked=per_rank * len(ranks), ranks=ranks,
                                  clips_of_each_rank=check, length="full 10 s", against="CPU port of the reference forward")
-        rec["clocks"] = ctx.sampler.window(t_sec0, time.perf_counter(), "cfg4 section")
+        rec["clocks"] = ctx.sampler.window(t_sec0, t_sec1, "cfg4: the timed forwards + the same forward looped to >= 1 s")
     del x, x_host, y_host
     model.release_engine()
     torch.cuda.empty_cache()
@@ -448,9 +472,9 @@ def run_cfg5(ctx, args):
     model = model.to(ctx.dev).eval()
     cond = torch.full((1, 2), 0.5, device=ctx.dev)
     rec = dict(workload="cfg5: cfg2 network as a stream, history of every block carried on the device", replicas=ctx.world)
-    t_sec0 = time.perf_counter()
     g = torch.Generator(device=ctx.dev).manual_seed(500 + ctx.rank)
     from neural_audio_spring_reverb_b200.streaming import CachedStream
+    windows = []
     for chunk, seconds in ((65536, args.cfg5_seconds), (1024, min(args.cfg5_seconds, 300.0))):
         n_chunks = max(4, int(seconds * SR) // chunk)
         total = n_chunks * chunk
@@ -463,6 +487,7 @@ def run_cfg5(ctx, args):
         eng = model._engine()
         l0 = eng.launch_count()
         barrier(ctx)
+        ctx.sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         ev0.record()
@@ -475,6 +500,8 @@ def run_cfg5(ctx, args):
         ev1.record()
         torch.cuda.synchronize(ctx.dev)
         wall = time.perf_counter() - t0
+        windows.append((t0, time.perf_counter()))
+        ctx.sampler.stop()
         dev_s = max_over_ranks(ctx, ev0.elapsed_time(ev1) * 1e-3)
         wall = max_over_ranks(ctx, wall)
         r = dict(chunk_samples=chunk, audio_seconds=total / SR, chunks=n_chunks,
@@ -493,7 +520,7 @@ def run_cfg5(ctx, args):
         rec[f"chunk_{chunk}"] = r
         del x, keep
     if ctx.rank == 0:
-        rec["clocks"] = ctx.sampler.window(t_sec0, time.perf_counter(), "cfg5 section")
+        rec["clocks"] = ctx.sampler.window(windows[0][0], windows[-1][1], "cfg5: the two timed streams")
     model.release_engine()
     torch.cuda.empty_cache()
     return rec
@@ -539,8 +566,12 @@ def main():
         build_native()
     if ctx.world > 1:
         dist.barrier()
-    from neural_audio_spring_reverb_b200 import hostaffinity
-    ctx.affinity = hostaffinity.pin_to_gpu(local, ctx.world)
+    # CPU pinning per rank is available (NASR_PIN=1) but off by default: measured on an 8-GPU box it does not help the
+    # synchronous host-tensor calls (profiles/r2_e2e_scale_8gpu.log: 7.79 G samples/s unpinned vs 7.44 G pinned)
+    ctx.affinity = dict(pinned=False, reason="off by default (NASR_PIN=1 enables)")
+    if os.environ.get("NASR_PIN", "0") == "1":
+        from neural_audio_spring_reverb_b200 import hostaffinity
+        ctx.affinity = hostaffinity.pin_to_gpu(local, ctx.world)
 
     model, arch, kw, T = build_model(args.workload)
     # one-time weight broadcast over NCCL: every rank ends up with rank 0's blob
@@ -557,9 +588,9 @@ def main():
     cond_host = cond.cpu().pin_memory()
     ctx.flush = torch.empty(256 << 20, dtype=torch.uint8, device=ctx.dev)   # > 126 MB L2
 
-    ctx.sampler = ClockSampler(local)
-    if ctx.rank == 0:
-        ctx.sampler.start()
+    ctx.sampler = ClockSampler(local, enabled=ctx.rank == 0)
+    ctx.sampler.start()
+    time.sleep(0.15)           # nvidia-smi start-up: the first sample should precede the timed steps
 
     # ---- device-resident timing (value) ----
     t_main0 = time.perf_counter()
@@ -584,6 +615,7 @@ def main():
         torch.cuda.synchronize(ctx.dev)
     model.set_async(None)
     t_main1 = time.perf_counter()
+    ctx.sampler.stop()         # not during the end-to-end leg (see ClockSampler.start)
 
     # ---- end to end through the public API with host buffers ----
     # every call is synchronous (H2D, forward, result written to the pinned output, stream sync); at least 50 calls so

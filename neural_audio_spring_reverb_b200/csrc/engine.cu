@@ -42,6 +42,10 @@ struct BlockState {
   float* w0 = nullptr;                       // first block: conv weights [k][Cin][W], original order
   uint16_t* wtc = nullptr;                   // tcgen05 paths: split-fp16 weight tiles (tc_pack_weights / ring_pack_weights)
   float inv_sw = 1.f, inv_sr = 1.f;
+  // ring blocks also keep the tap-gather packing: a launch with only a few tiles per SM (short streaming chunks) pays
+  // the ring's k - 1 warm-up steps per span in full, the tap-gather kernel has no warm-up
+  uint16_t* wtg = nullptr;
+  float g_inv_sw = 1.f, g_inv_sr = 1.f;
   uint16_t* wtoep = nullptr;                 // first block on the tensor cores (toep_pack_weights)
   int toep_kp = 0;
   float toep_inv_sw = 1.f, toep_inv_sr = 1.f;
@@ -71,6 +75,7 @@ struct nasr_engine {
   volatile unsigned int* sat_host = nullptr;   // [kSatWords]
   unsigned int* sat_cur = nullptr;             // device alias of the current call's word
   uint64_t sat_gen = 0;
+  size_t sat_idx = 0;                          // word of the last call
   DevBuf plane[2];
   // streaming
   int streamB = 0;
@@ -84,6 +89,13 @@ struct nasr_engine {
   cudaStream_t hs_in = nullptr, hs_out = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   DevBuf hx2[2], hy2[2];
+  bool small_gather = true;   // NASR_SMALL_GATHER=0: ring kernel for every launch size (dev)
+  bool stream_graph = true;   // NASR_STREAM_GRAPH=0: streaming chunks as plain launches (dev)
+  // streaming: CUDA graphs of one chunk's launches, keyed by (B, T_chunk); x is staged into plane 0 and y leaves through
+  // ychunk by plain device copies around the graph launch, so the graph's kernel arguments never change
+  struct ChunkGraph { int B = 0; long long Tc = 0; int seen = 0, launches = 0; cudaGraphExec_t exec = nullptr; bool failed = false; };
+  std::vector<ChunkGraph> graphs;
+  DevBuf ychunk;
   bool host_pipe = true;   // NASR_HOST_PIPE=0: whole batch in one H2D / forward / D2H sequence (dev)
   size_t budget_bytes = (size_t)24 << 30;
   mutable std::string err;
@@ -104,13 +116,16 @@ int fail(nasr_engine* e, int code, const std::string& msg) {
 }
 
 // start of a call that may raise the saturation flag: pick and clear its word
+// (word 0 is the stream's: chunks raise it until the next nasr_stream_reset - a CUDA graph bakes its address in)
 inline void sat_begin(nasr_engine* e) {
   e->sat_gen += 1;
-  const size_t idx = (size_t)(e->sat_gen % kSatWords);
+  const size_t idx = 1 + (size_t)(e->sat_gen % (kSatWords - 1));
   e->sat_host[idx] = 0;
   e->sat_cur = e->sat_flag + idx;
+  e->sat_idx = idx;
 }
-inline volatile unsigned int& sat_word(nasr_engine* e) { return e->sat_host[e->sat_gen % kSatWords]; }
+inline void sat_stream(nasr_engine* e) { e->sat_cur = e->sat_flag; e->sat_idx = 0; }
+inline volatile unsigned int& sat_word(nasr_engine* e) { return e->sat_host[e->sat_idx]; }
 
 inline int check_clips(nasr_engine* e, int B) {
   if (B < 1) return fail(e, NASR_ERR_INVALID, "B must be >= 1");
@@ -211,6 +226,8 @@ void free_block(BlockState& b) {
   b.perm = nullptr;
   if (b.wtc) cudaFree(b.wtc);
   b.wtc = nullptr;
+  if (b.wtg) cudaFree(b.wtg);
+  b.wtg = nullptr;
   if (b.w0) cudaFree(b.w0);
   b.w0 = nullptr;
   if (b.wtoep) cudaFree(b.wtoep);
@@ -243,16 +260,23 @@ BlockArgs make_args(const nasr_engine* e, int i, int B, bool tc = true) {
 int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool allow_tc = true, bool tc_chain = true) {
   const BlockState& bs = e->blocks[i];
   cudaError_t err;
-  if (allow_tc && tc_chain && bs.path == 1) {
+  // tiles of 128 samples in this launch: with fewer than ~2 per SM the ring kernel's warm-up (k - 1 steps per span)
+  // costs more than the tap-gather kernel's smaller instructions (measured on cfg2 streams: 1 024-sample chunks 110 vs
+  // 129 us per chunk with the tap-gather kernel, 65 536-sample chunks 172 vs 166 us)
+  const long long tiles = (long long)a.B * ((a.T + 127) / 128);
+  const bool small_launch = bs.path == 2 && bs.wtg && e->small_gather && tiles < 2LL * e->sm_count;
+  if (allow_tc && tc_chain && (bs.path == 1 || small_launch)) {
     TcLaunch L{};
     L.cache = &e->tc_cache[i];
     L.in = a.in; L.in_rows = a.in_rows; L.in_clip_stride_elems = a.in_clip_stride;
-    L.wpacked = bs.wtc; L.arch = e->desc.arch; L.sm_count = e->sm_count;
+    L.wpacked = small_launch ? bs.wtg : bs.wtc; L.arch = e->desc.arch; L.sm_count = e->sm_count;
     TcArgs& t = L.a;
     t.out = a.out; t.out_fmt = a.out_fmt; t.out_clip_stride = a.out_clip_stride; t.out_rows = a.out_rows;
     t.out_row0 = a.out_row0; t.in_row0 = a.in_row0; t.B = a.B; t.T = a.T; t.k = a.k; t.d = a.d;
     t.scale = a.scale; t.shift = a.shift; t.slope = a.slope;
-    t.inv_sw = bs.inv_sw * kActInv; t.inv_sr = bs.inv_sr * kActInv;   // the input plane holds value * kActScale
+    // the input plane holds value * kActScale
+    t.inv_sw = (small_launch ? bs.g_inv_sw : bs.inv_sw) * kActInv;
+    t.inv_sr = (small_launch ? bs.g_inv_sr : bs.inv_sr) * kActInv;
     t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_cur; t.prof = a.prof;
     err = launch_tc_block(L, s);
   } else if (allow_tc && tc_chain && bs.path == 2) {
@@ -331,7 +355,8 @@ void nasr_engine_destroy(nasr_engine* e) {
     if (e->sat_host) cudaFreeHost((void*)e->sat_host);
     release(e->plane[0]); release(e->plane[1]);
     for (auto& p : e->splane) release(p);
-    release(e->scratch); release(e->sfinal); release(e->hx); release(e->hy); release(e->hc);
+    release(e->scratch); release(e->sfinal); release(e->hx); release(e->hy); release(e->hc); release(e->ychunk);
+    for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (int q = 0; q < 2; ++q) {
       release(e->hx2[q]); release(e->hy2[q]);
       if (e->ev_in[q]) cudaEventDestroy(e->ev_in[q]);
@@ -387,6 +412,8 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
   if (const char* env = getenv("NASR_PDL")) e->pdl = atoi(env) != 0;
   if (const char* env = getenv("NASR_ZEROCOPY")) e->zero_copy = atoi(env) != 0;
   if (const char* env = getenv("NASR_HOST_PIPE")) e->host_pipe = atoi(env) != 0;
+  if (const char* env = getenv("NASR_SMALL_GATHER")) e->small_gather = atoi(env) != 0;
+  if (const char* env = getenv("NASR_STREAM_GRAPH")) e->stream_graph = atoi(env) != 0;
   const float* p = w;
   std::vector<FoldArgs> fold(n);
   int rc = NASR_OK;
@@ -484,6 +511,11 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
         h_wtc.insert(h_wtc.end(), part.begin(), part.end());
       }
       up(&b.wtc, h_wtc);
+      if (tc_eligible(desc->arch, C, C, k) && !b.split_out) {
+        std::vector<uint16_t> h_wtg;
+        tc_pack_weights(desc->arch, k, conv_w, res_w, h_wtg, &b.g_inv_sw, &b.g_inv_sr);
+        up(&b.wtg, h_wtg);
+      }
     }
     if (desc->has_film) {
       if (h_adw.empty()) h_adw.push_back(0.f);  // cond_dim == 0: Linear(0, 2W) is bias only
@@ -518,6 +550,7 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
 }
 
 static int set_cond_impl(nasr_engine* e, const float* cond_dev, const float* cond_inline_host, int B, void* stream);
+static void drop_chunk_graphs(nasr_engine* e);
 
 int nasr_set_cond(nasr_engine* e, const float* cond_dev, int B, void* stream) {
   return set_cond_impl(e, cond_dev, nullptr, B, stream);
@@ -553,6 +586,7 @@ static int set_cond_impl(nasr_engine* e, const float* cond_dev, const float* con
     }
     e->fold_valid = false;
     e->condB = 0;
+    drop_chunk_graphs(e);   // captured kernels hold the old table pointers
     for (int i = 0; i < n; ++i) {
       BlockState& b = e->blocks[i];
       if (b.scale) cudaFree(b.scale);
@@ -947,6 +981,7 @@ static int stream_alloc(nasr_engine* e, int B, long long Tcap, cudaStream_t s, b
     for (auto& q : np) release(q);
     return fail(e, NASR_ERR_CUDA, std::string("stream plane set-up: ") + cudaGetErrorString(cerr));
   }
+  drop_chunk_graphs(e);
   for (auto& q : e->splane) release(q);
   e->splane = np;
   e->streamB = B;
@@ -960,13 +995,93 @@ int nasr_stream_reset(nasr_engine* e, int B, void* stream) {
   DeviceGuard guard(e->device);
   cudaStream_t s = (cudaStream_t)stream;
   NASR_CUDA(e, cudaStreamSynchronize(s));
-  sat_begin(e);
+  e->sat_host[0] = 0;
+  sat_stream(e);
   const long long Tcap = (e->streamB == B && e->streamTcap > 0) ? e->streamTcap : 1024;
   if (e->streamB == B && !e->splane.empty()) {
     for (auto& q : e->splane) NASR_CUDA(e, cudaMemsetAsync(q.p, 0, q.cap, s));
     return NASR_OK;
   }
   return stream_alloc(e, B, Tcap, s, false);
+}
+
+static void drop_chunk_graphs(nasr_engine* e) {
+  for (auto& g : e->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+}
+
+// One chunk's kernels on `s`: the blocks (plane i -> plane i + 1, the last one -> y_out [B][out_ch][Tc]) and the history
+// carry.  Everything it touches is engine-owned and allocated beforehand, so the sequence can be captured into a graph.
+static int chunk_body(nasr_engine* e, float* y_out, int B, int64_t Tc, cudaStream_t s) {
+  const int n = (int)e->blocks.size();
+  const long long Tcap = e->streamTcap;
+  const long long rb = (long long)plane_row_bytes(e);
+  const int in_ch = e->desc.in_ch;
+  for (int i = 0; i < n; ++i) {
+    const BlockState& bs = e->blocks[i];
+    BlockArgs a = make_args(e, i, B);
+    a.T = Tc;
+    a.in = e->splane[i].p;
+    a.in_row0 = bs.hist;
+    a.in_rows = bs.hist + Tcap;
+    if (i == 0) a.in_clip_stride = (long long)in_ch * a.in_rows;
+    else a.in_clip_stride = a.in_rows * e->Cp * (bs.in_fmt == FMT_SPLIT16 ? 2 : 1);
+    if (i == n - 1 && bs.split_out) {
+      a.out = e->sfinal.p; a.out_rows = Tc; a.out_row0 = 0; a.out_clip_stride = Tc * e->Cp;
+    } else if (i == n - 1) {
+      a.out = y_out; a.out_clip_stride = (long long)e->desc.out_ch * Tc; a.out_rows = Tc; a.out_row0 = 0;
+    } else {
+      const BlockState& nx = e->blocks[i + 1];
+      a.out = e->splane[i + 1].p;
+      a.out_rows = nx.hist + Tcap; a.out_row0 = nx.hist;
+      a.out_clip_stride = a.out_rows * e->Cp * (bs.out_fmt == FMT_SPLIT16 ? 2 : 1);
+    }
+    int rc = launch_block(e, a, i, s);
+    if (rc != NASR_OK) return rc;
+    if (i == n - 1 && bs.split_out) {
+      NASR_CUDA(e, launch_out_net((const float*)e->sfinal.p, Tc * e->Cp, 0, e->Cp, e->C, e->wout, e->desc.out_ch,
+                                  e->desc.final_tanh, y_out, (long long)e->desc.out_ch * Tc, Tc, 0, B, Tc, e->sm_count, s, nullptr));
+      e->launches += 1;
+    }
+  }
+  // carry (wrapper.py:23-30): rows [Tc, Tc + hist) -> [0, hist) of every plane.  Planes whose chunk is at least as long
+  // as their history move directly; where source and destination overlap (Tc < hist) the rows go through scratch.
+  // Two batched launches at most: {overlapping -> scratch}, then {direct moves, scratch -> planes}.
+  std::vector<CopyJob> first, second;
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    const BlockState& bs = e->blocks[i];
+    if (bs.hist == 0) continue;
+    const long long rows = bs.hist + Tcap;
+    const int rbytes = (i == 0) ? 4 : (int)rb;
+    const long long stride = rows * rbytes;
+    const int segs = (i == 0) ? B * in_ch : B;
+    CopyJob j{};
+    j.src = (const char*)e->splane[i].p + Tc * rbytes;
+    j.dst = (char*)e->splane[i].p;
+    j.src_stride = stride; j.dst_stride = stride;
+    j.n_bytes = bs.hist * rbytes;
+    j.segs = segs;
+    if (Tc >= bs.hist) {
+      second.push_back(j);
+    } else {
+      CopyJob a = j, b = j;
+      a.dst = (char*)e->scratch.p + off; a.dst_stride = j.n_bytes;
+      b.src = (const char*)e->scratch.p + off; b.src_stride = j.n_bytes;
+      off += ((size_t)segs * j.n_bytes + 15) & ~(size_t)15;
+      first.push_back(a);
+      second.push_back(b);
+    }
+  }
+  for (auto* jobs : {&first, &second}) {
+    for (size_t q = 0; q < jobs->size(); q += NASR_MULTI_COPY_MAX) {
+      const int cnt = (int)(jobs->size() - q < NASR_MULTI_COPY_MAX ? jobs->size() - q : NASR_MULTI_COPY_MAX);
+      NASR_CUDA(e, launch_copy_multi(jobs->data() + q, cnt, s));
+      e->launches += 1;
+    }
+  }
+  return NASR_OK;
 }
 
 int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev, int B, int64_t Tc, void* stream) {
@@ -988,88 +1103,80 @@ int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev, int B, 
     int rc = stream_alloc(e, B, Tc, s, true);
     if (rc != NASR_OK) return rc;
   }
-  sat_begin(e);
   const int n = (int)e->blocks.size();
   const long long Tcap = e->streamTcap;
   const long long rb = (long long)plane_row_bytes(e);
   const int in_ch = e->desc.in_ch;
-  // stage the chunk behind block 0's history
+  // engine-owned buffers the chunk's kernels use besides the planes (growing them invalidates captured graphs)
+  {
+    size_t need_final = 0, need_scratch = 0;
+    if (e->blocks[n - 1].split_out) need_final = (size_t)B * Tc * rb + plane_slack_bytes();
+    for (int i = 0; i < n; ++i) {
+      const BlockState& bs = e->blocks[i];
+      if (bs.hist == 0 || Tc >= bs.hist) continue;
+      const size_t segs = (i == 0) ? (size_t)B * in_ch : (size_t)B;
+      need_scratch += (segs * bs.hist * ((i == 0) ? 4 : (size_t)rb) + 15) & ~(size_t)15;
+    }
+    const size_t need_y = (size_t)B * e->desc.out_ch * Tc * sizeof(float);
+    if (e->sfinal.cap < need_final || e->scratch.cap < need_scratch || e->ychunk.cap < need_y) {
+      NASR_CUDA(e, cudaStreamSynchronize(s));
+      drop_chunk_graphs(e);
+      NASR_CUDA(e, ensure(e->sfinal, need_final));
+      NASR_CUDA(e, ensure(e->scratch, need_scratch));
+      NASR_CUDA(e, ensure(e->ychunk, need_y));
+    }
+  }
+  sat_stream(e);
+  // stage the chunk behind block 0's history: [B * in_ch] rows of Tc floats into rows of hist + Tcap floats
   {
     const BlockState& b0 = e->blocks[0];
-    NASR_CUDA(e, launch_copy_rows(x_dev, Tc * 4, 0, e->splane[0].p, (b0.hist + Tcap) * 4, b0.hist, Tc, 4, B * in_ch, s));
-    e->launches += 1;
+    NASR_CUDA(e, cudaMemcpy2DAsync((char*)e->splane[0].p + b0.hist * 4, (size_t)(b0.hist + Tcap) * 4, x_dev, (size_t)Tc * 4,
+                                   (size_t)Tc * 4, (size_t)B * in_ch, cudaMemcpyDeviceToDevice, s));
   }
-  for (int i = 0; i < n; ++i) {
-    const BlockState& bs = e->blocks[i];
-    BlockArgs a = make_args(e, i, B);
-    a.T = Tc;
-    a.in = e->splane[i].p;
-    a.in_row0 = bs.hist;
-    if (i == 0) {
-      a.in_rows = bs.hist + Tcap; a.in_clip_stride = (long long)in_ch * a.in_rows;
-    } else {
-      a.in_rows = bs.hist + Tcap;
-      a.in_clip_stride = a.in_rows * e->Cp * (bs.in_fmt == FMT_SPLIT16 ? 2 : 1);
+  const size_t ybytes = (size_t)B * e->desc.out_ch * Tc * sizeof(float);
+  nasr_engine::ChunkGraph* g = nullptr;
+  if (e->stream_graph) {
+    for (auto& q : e->graphs)
+      if (q.B == B && q.Tc == Tc) g = &q;
+    if (!g) {
+      if (e->graphs.size() >= 8) drop_chunk_graphs(e);   // a handful of chunk sizes per stream is the normal case
+      e->graphs.emplace_back();
+      g = &e->graphs.back();
+      g->B = B; g->Tc = Tc;
     }
-    if (i == n - 1 && bs.split_out) {
-      const size_t need = (size_t)B * Tc * rb + plane_slack_bytes();
-      if (e->sfinal.cap < need) {
-        NASR_CUDA(e, cudaStreamSynchronize(s));
-        NASR_CUDA(e, ensure(e->sfinal, need));
-      }
-      a.out = e->sfinal.p; a.out_rows = Tc; a.out_row0 = 0; a.out_clip_stride = Tc * e->Cp;
-    } else if (i == n - 1) {
-      a.out = y_dev; a.out_clip_stride = (long long)e->desc.out_ch * Tc; a.out_rows = Tc; a.out_row0 = 0;
-    } else {
-      const BlockState& nx = e->blocks[i + 1];
-      a.out = e->splane[i + 1].p;
-      a.out_rows = nx.hist + Tcap; a.out_row0 = nx.hist;
-      a.out_clip_stride = a.out_rows * e->Cp * (bs.out_fmt == FMT_SPLIT16 ? 2 : 1);
+  }
+  int rc = NASR_OK;
+  if (g && g->exec) {
+    NASR_CUDA(e, cudaGraphLaunch(g->exec, s));
+    e->launches += g->launches;
+  } else if (g && !g->failed && g->seen >= 1) {
+    // second chunk of this shape: everything is allocated and every kernel attribute set - capture the sequence
+    const int64_t l0 = e->launches;
+    cudaGraph_t graph = nullptr;
+    cudaError_t cerr = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);
+    if (cerr == cudaSuccess) {
+      rc = chunk_body(e, (float*)e->ychunk.p, B, Tc, s);
+      cerr = cudaStreamEndCapture(s, &graph);
+      if (rc == NASR_OK && cerr == cudaSuccess) cerr = cudaGraphInstantiate(&g->exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
     }
-    int rc = launch_block(e, a, i, s);
+    if (rc != NASR_OK || cerr != cudaSuccess || !g->exec) {
+      cudaGetLastError();
+      g->failed = true;
+      g->exec = nullptr;
+      e->launches = l0;
+      rc = chunk_body(e, (float*)e->ychunk.p, B, Tc, s);   // plain launches from now on for this shape
+      if (rc != NASR_OK) return rc;
+    } else {
+      g->launches = (int)(e->launches - l0);
+      NASR_CUDA(e, cudaGraphLaunch(g->exec, s));
+    }
+  } else {
+    rc = chunk_body(e, (float*)e->ychunk.p, B, Tc, s);
     if (rc != NASR_OK) return rc;
-    if (i == n - 1 && bs.split_out) {
-      NASR_CUDA(e, launch_out_net((const float*)e->sfinal.p, Tc * e->Cp, 0, e->Cp, e->C, e->wout, e->desc.out_ch,
-                                  e->desc.final_tanh, y_dev, (long long)e->desc.out_ch * Tc, Tc, 0, B, Tc, e->sm_count, s, nullptr));
-      e->launches += 1;
-    }
+    if (g) g->seen += 1;
   }
-  // carry: rows [Tc, Tc + hist) -> [0, hist) of every plane.  Planes whose chunk is at least as long as the history
-  // (source and destination do not overlap) are moved by ONE batched copy launch; shorter chunks go through scratch.
-  std::vector<CopyJob> jobs;
-  for (int i = 0; i < n; ++i) {
-    const BlockState& bs = e->blocks[i];
-    if (bs.hist == 0) continue;
-    const long long rows = bs.hist + Tcap;
-    const long long stride = (i == 0) ? rows * 4 : rows * rb;
-    const int rbytes = (i == 0) ? 4 : (int)rb;
-    const int segs = (i == 0) ? B * in_ch : B;
-    if (Tc >= bs.hist && (int)jobs.size() < NASR_MULTI_COPY_MAX) {
-      CopyJob j{};
-      j.src = (const char*)e->splane[i].p + Tc * rbytes;
-      j.dst = (char*)e->splane[i].p;
-      j.src_stride = stride; j.dst_stride = stride;
-      j.n_bytes = bs.hist * rbytes;
-      j.segs = segs;
-      jobs.push_back(j);
-    } else if (Tc >= bs.hist) {
-      NASR_CUDA(e, launch_copy_rows(e->splane[i].p, stride, Tc, e->splane[i].p, stride, 0, bs.hist, rbytes, segs, s));
-      e->launches += 1;
-    } else {
-      const size_t need = (size_t)segs * bs.hist * rbytes;
-      if (e->scratch.cap < need) {
-        NASR_CUDA(e, cudaStreamSynchronize(s));
-        NASR_CUDA(e, ensure(e->scratch, need));
-      }
-      NASR_CUDA(e, launch_copy_rows(e->splane[i].p, stride, Tc, e->scratch.p, bs.hist * rbytes, 0, bs.hist, rbytes, segs, s));
-      NASR_CUDA(e, launch_copy_rows(e->scratch.p, bs.hist * rbytes, 0, e->splane[i].p, stride, 0, bs.hist, rbytes, segs, s));
-      e->launches += 2;
-    }
-  }
-  if (!jobs.empty()) {
-    NASR_CUDA(e, launch_copy_multi(jobs.data(), (int)jobs.size(), s));
-    e->launches += 1;
-  }
+  NASR_CUDA(e, cudaMemcpyAsync(y_dev, e->ychunk.p, ybytes, cudaMemcpyDeviceToDevice, s));
   return NASR_OK;
 }
 

@@ -176,10 +176,17 @@ class FusedNetMixin:
             y = torch.empty((B, self.out_ch, T), device=dev, dtype=torch.float32)
             stream = torch.cuda.current_stream(dev).cuda_stream
             cptr = 0
+            cc = None
             if cond is not None:
                 cc = cond.detach().to(device=dev, dtype=torch.float32).contiguous()
                 cptr = cc.data_ptr()
-            eng.set_cond(cptr, B, stream)
+            # streaming: the same (unmodified) cond tensor chunk after chunk needs no new fold.  The tensor is kept alive
+            # so that its address cannot be recycled for another cond behind our back.
+            key = (eng, cptr, cc._version if cc is not None else 0, B, stream)
+            if not (chunk and self.__dict__.get("_nasr_cond_key") == key):
+                eng.set_cond(cptr, B, stream)
+                self.__dict__["_nasr_cond_key"] = key if chunk else None
+                self.__dict__["_nasr_cond_ref"] = cc if chunk else None
             if T > 0:
                 if chunk:
                     eng.forward_chunk(xc.data_ptr(), y.data_ptr(), B, T, stream)
@@ -204,6 +211,7 @@ class FusedNetMixin:
             return self._nasr_run(xd, cond, True).cpu()
         # pinned result: the engine's last kernel writes it directly (zero-copy), see nasr_forward_host
         y = torch.empty((B, self.out_ch, T), dtype=torch.float32, pin_memory=True)
+        self.__dict__["_nasr_cond_key"] = None          # the host path folds its own cond
         eng.forward_host(xc.data_ptr(), cptr, y.data_ptr(), B, T, stream)
         return y
 
@@ -253,6 +261,7 @@ class FusedNetMixin:
         if self._nasr_has_film() and self.cond_dim > 0:
             cc = cond.detach().to(device=dev, dtype=torch.float32).contiguous()
             cptr = cc.data_ptr()
+        self.__dict__["_nasr_cond_key"] = None
         eng.set_cond(cptr, B, stream)
         if T > 0:
             eng.block_forward(index, xc.data_ptr(), y.data_ptr(), B, T, stream)
