@@ -25,6 +25,9 @@
  *   nasr_postprocess       <- the post-processing of make_inference: peak normalise,
  *                             torchaudio highpass_biquad (lfilter, clamp), peak normalise
  *                             (src/nasr/inference.py:70-78)
+ *   nasr_eval_metrics      <- the MAE / ESR / DC metrics of evaluate_model (src/nasr/eval.py:38-40,118-121)
+ *   nasr_rt60              <- measure_rt60's Schroeder integration (src/nasr/tools/rt60.py:49-70)
+ *   nasr_convolve_full     <- the direct convolution of measure_model_ir (src/nasr/tools/ir_model.py:138-140)
  *
  * Conventions
  *   - All tensors are fp32, contiguous, reference layout: x [B, in_ch, T],
@@ -181,6 +184,37 @@ NASR_API int nasr_block_forward(nasr_engine* e, int block, const float* x_dev, f
 NASR_API size_t nasr_postprocess_workspace_bytes(int rows, int64_t T);
 NASR_API int nasr_postprocess(const float* y_dev, float* out_dev, int rows, int64_t T, const float* b_coeffs,
                      const float* a_coeffs, int clamp, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/*
+ * Evaluation metrics of evaluate_model on the device (eval.py:38-40,118-121), one pass over (pred, target):
+ *   out_dev[0] = torch.nn.L1Loss()(pred, target)            mean |pred - target| over all elements
+ *   out_dev[1] = auraloss.time.ESRLoss()(pred, target)      mean over rows of sum (t - p)^2 / (sum t^2 + 1e-8)
+ *   out_dev[2] = auraloss.time.DCLoss()(pred, target)       mean over rows of mean(t - p)^2 / (mean t^2 + 1e-8)
+ * pred_dev / target_dev: [rows, T] fp32 (rows = batch x channels); out_dev: 3 doubles on the device.
+ * (auraloss 0.4.0 is a third-party dependency that is absent here: its published formulas are restated, parity
+ * unpinned. The mel-scaled multi-resolution STFT loss of eval.py:41-49 is not built.)
+ */
+NASR_API size_t nasr_eval_metrics_workspace_bytes(int rows);
+NASR_API int nasr_eval_metrics(const float* pred_dev, const float* target_dev, int rows, int64_t T, double* out_dev,
+                      void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/*
+ * RT60 of an impulse response by Schroeder integration (tools/rt60.py:49-70): energy[i] = sum_{j >= i} h[j]^2,
+ * truncated before its last nonzero sample, in dB relative to energy[0]; t_5 / t_decay = first samples below -5 dB /
+ * -decay_db; rt60 = (60 / decay_db) * (t_decay - t_5), 0 when a crossing does not exist (the reference's except branch).
+ * out_dev: 4 doubles {rt60 seconds, i_5db, i_decay, i_nz} (-1 = not found). The reference sums in fp32; here fp64.
+ */
+NASR_API size_t nasr_rt60_workspace_bytes(int64_t n);
+NASR_API int nasr_rt60(const float* h_dev, int64_t n, double sample_rate, double decay_db, double* out_dev,
+              void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/*
+ * Full linear convolution out[i] = sum_j a[j] * b[i - j], i in [0, n + m - 1), fp64 multiply-adds: the
+ * scipy.signal.convolve(..., method="direct") of measure_model_ir (tools/ir_model.py:138-140) as a hand-written
+ * direct (O(n m)) kernel. a_dev [n], b_dev [m], out_dev [n + m - 1]: doubles on the current device.
+ */
+NASR_API int nasr_convolve_full(const double* a_dev, int64_t n, const double* b_dev, int64_t m, double* out_dev,
+                       void* stream);
 
 /* Bytes of device workspace the engine holds / would hold for (B, T). */
 NASR_API size_t nasr_workspace_bytes(const nasr_engine* e, int B, int64_t T);

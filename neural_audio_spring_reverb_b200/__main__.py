@@ -1,11 +1,12 @@
-"""CLI: the `infer`, `rtf` and `ir` actions of nafx-springrev
+"""CLI: the `infer`, `rtf`, `ir` and `rt60` actions of nafx-springrev
 (src/neural_audio_spring_reverb/__main__.py:5-184) on the B200 engine.
-The other actions (train, eval, download, wrap, ...) are not part of this package."""
+The other actions (train, eval, download, wrap, ...) are not part of this package (the metrics of `eval` are
+available as neural_audio_spring_reverb_b200.eval.evaluate_batch / evaluate_model for callers that bring a test set)."""
 import argparse
 
 import torch
 
-ACTIONS = ["infer", "rtf", "ir"]
+ACTIONS = ["infer", "rtf", "ir", "rt60"]
 
 
 def main(argv=None):
@@ -24,6 +25,12 @@ def main(argv=None):
         args.device = torch.device("cuda:0")
     else:
         args.device = torch.device(args.device)
+    if args.action == "rt60":
+        from .tools.rt60 import measure_rt60
+        if args.input is None:
+            parser.error("-i/--input is required for rt60")
+        measure_rt60(args)
+        return
     if args.checkpoint is None:
         parser.error("-c/--checkpoint is required")
 

@@ -23,7 +23,8 @@ EXPORTS = (
     "nasr_set_cond", "nasr_forward", "nasr_forward_checked", "nasr_sat_fallbacks", "nasr_forward_profiled", "nasr_saturated", "nasr_forward_host", "nasr_stream_reset",
     "nasr_forward_chunk", "nasr_block_forward", "nasr_workspace_bytes",
     "nasr_receptive_field", "nasr_launch_count", "nasr_block_path", "nasr_version",
-    "nasr_postprocess", "nasr_postprocess_workspace_bytes", "nasr_debug_ring_stamps", "nasr_debug_ring_steps", "nasr_debug_ring_plan", "nasr_debug_toep_stamps",
+    "nasr_postprocess", "nasr_postprocess_workspace_bytes", "nasr_eval_metrics", "nasr_eval_metrics_workspace_bytes",
+    "nasr_rt60", "nasr_rt60_workspace_bytes", "nasr_convolve_full", "nasr_debug_ring_stamps", "nasr_debug_ring_steps", "nasr_debug_ring_plan", "nasr_debug_toep_stamps",
 )
 
 
@@ -93,6 +94,16 @@ def load_library():
     lib.nasr_postprocess_workspace_bytes.argtypes = [i32, i64]
     lib.nasr_postprocess.restype = i32
     lib.nasr_postprocess.argtypes = [f32p, f32p, i32, i64, C.c_void_p, C.c_void_p, i32, vp, C.c_size_t, vp]
+    lib.nasr_eval_metrics_workspace_bytes.restype = C.c_size_t
+    lib.nasr_eval_metrics_workspace_bytes.argtypes = [i32]
+    lib.nasr_eval_metrics.restype = i32
+    lib.nasr_eval_metrics.argtypes = [f32p, f32p, i32, i64, vp, vp, C.c_size_t, vp]
+    lib.nasr_rt60_workspace_bytes.restype = C.c_size_t
+    lib.nasr_rt60_workspace_bytes.argtypes = [i64]
+    lib.nasr_rt60.restype = i32
+    lib.nasr_rt60.argtypes = [f32p, i64, C.c_double, C.c_double, vp, vp, C.c_size_t, vp]
+    lib.nasr_convolve_full.restype = i32
+    lib.nasr_convolve_full.argtypes = [vp, i64, vp, i64, vp, vp]
     lib.nasr_debug_ring_plan.restype = i32
     lib.nasr_debug_ring_plan.argtypes = [i32, i32, i32, i32, i64, i64, i32, C.c_void_p]
     lib.nasr_debug_ring_steps.restype = i32
@@ -238,6 +249,78 @@ def postprocess(y, b_coeffs, a_coeffs, clamp: bool = True):
     if rc != NASR_OK:
         raise (ValueError if rc == NASR_ERR_INVALID else RuntimeError)(f"nasr_postprocess failed (nasr_status {rc})")
     return out.reshape(shape)
+
+
+def _status(rc: int, what: str):
+    if rc != NASR_OK:
+        raise (ValueError if rc == NASR_ERR_INVALID else RuntimeError)(f"{what} failed (nasr_status {rc})")
+
+
+def eval_metrics(pred, target):
+    """eval.py:38-40,118-121 on the device: pred / target [B, C, T] (or [rows, T]) fp32 CUDA tensors ->
+    {"eval/mae", "eval/esr", "eval/dc"} as Python floats (one fused reduction over both tensors)."""
+    import torch
+
+    lib = load_library()
+    if not (pred.is_cuda and target.is_cuda):
+        raise RuntimeError("nasr_eval_metrics runs on the device only (no CPU path)")
+    if pred.shape != target.shape:
+        raise ValueError(f"pred {tuple(pred.shape)} and target {tuple(target.shape)} differ in shape")
+    p = pred.detach().reshape(-1, pred.shape[-1]).contiguous().float()
+    t = target.detach().reshape(-1, target.shape[-1]).to(p.device).contiguous().float()
+    rows, T = p.shape
+    out = torch.empty(3, dtype=torch.float64, device=p.device)
+    ws_bytes = int(lib.nasr_eval_metrics_workspace_bytes(rows))
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=p.device)
+    with torch.cuda.device(p.device):
+        stream = torch.cuda.current_stream(p.device).cuda_stream
+        _status(lib.nasr_eval_metrics(p.data_ptr(), t.data_ptr(), rows, T, out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                      stream or None), "nasr_eval_metrics")
+    mae, esr, dc = out.cpu().tolist()
+    return {"eval/mae": mae, "eval/esr": esr, "eval/dc": dc}
+
+
+def rt60(h, sample_rate: float, decay_db: float = 60.0):
+    """tools/rt60.py:49-70 on the device: h = impulse response (1-D fp32 CUDA tensor) ->
+    dict(rt60 seconds, i_5db, i_decay, i_nz)."""
+    import torch
+
+    lib = load_library()
+    if not h.is_cuda:
+        raise RuntimeError("nasr_rt60 runs on the device only (no CPU path)")
+    hc = h.detach().reshape(-1).contiguous().float()
+    n = hc.numel()
+    if n < 1:
+        raise ValueError("empty impulse response")
+    out = torch.empty(4, dtype=torch.float64, device=hc.device)
+    ws_bytes = int(lib.nasr_rt60_workspace_bytes(n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=hc.device)
+    with torch.cuda.device(hc.device):
+        stream = torch.cuda.current_stream(hc.device).cuda_stream
+        _status(lib.nasr_rt60(hc.data_ptr(), n, float(sample_rate), float(decay_db), out.data_ptr(), ws.data_ptr(),
+                              ws_bytes, stream or None), "nasr_rt60")
+    r, i5, idec, inz = out.cpu().tolist()
+    return dict(rt60=r, i_5db=int(i5), i_decay=int(idec), i_nz=int(inz))
+
+
+def convolve_full(a, b):
+    """scipy.signal.convolve(a, b, method="direct") on the device: 1-D float64 CUDA tensors -> [n + m - 1] float64."""
+    import torch
+
+    lib = load_library()
+    if not (a.is_cuda and b.is_cuda):
+        raise RuntimeError("nasr_convolve_full runs on the device only (no CPU path)")
+    ac = a.detach().reshape(-1).contiguous().double()
+    bc = b.detach().reshape(-1).to(ac.device).contiguous().double()
+    n, m = ac.numel(), bc.numel()
+    if n < 1 or m < 1:
+        raise ValueError("empty operand")
+    out = torch.empty(n + m - 1, dtype=torch.float64, device=ac.device)
+    with torch.cuda.device(ac.device):
+        stream = torch.cuda.current_stream(ac.device).cuda_stream
+        _status(lib.nasr_convolve_full(ac.data_ptr(), n, bc.data_ptr(), m, out.data_ptr(), stream or None),
+                "nasr_convolve_full")
+    return out
 
 
 def version() -> str:

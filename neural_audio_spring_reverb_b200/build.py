@@ -12,7 +12,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libnasr_b200.so"
-SOURCES = ["engine.cu", "generic_block.cu", "first_block.cu", "fold.cu", "tc_block.cu", "ring_block.cu", "toep_block.cu", "postproc.cu"]
+SOURCES = ["engine.cu", "generic_block.cu", "first_block.cu", "fold.cu", "tc_block.cu", "ring_block.cu", "toep_block.cu", "postproc.cu", "analysis.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -3,14 +3,15 @@
 
 The reference convolves the 240 000-sample model output with the 240 000-sample inverse filter with
 scipy.signal.convolve(method="direct"): 5.8e10 multiply-adds on one host core.  Here the model runs on the B200
-engine (make_inference) and the deconvolution is a linear convolution through cuFFT in float64 on the device
-(torch.fft - library code, O(N log N)); the normalisations of ir_model.py:128-146 are done in float64 as numpy does.
-Plots (matplotlib) are not part of this package."""
+engine (make_inference) and the deconvolution is the same direct linear convolution as a hand-written fp64 kernel
+(`nasr_convolve_full`, csrc/analysis.cu: ~15 ms for the 5 s sweep); the normalisations of ir_model.py:128-146 are done
+in float64 as numpy does.  Plots (matplotlib) are not part of this package."""
 from pathlib import Path
 
 import numpy as np
 import torch
 
+from .. import _native
 from ..inference import make_inference, _write_wav
 from ..networks.model_utils import load_model_checkpoint
 from .ir_signals import generate_reference
@@ -24,9 +25,7 @@ def deconvolve(sweep_output, inverse_filter, device) -> torch.Tensor:
     a = a - a.mean()
     a = a / a.abs().max()
     b = b / b.abs().max()
-    n = a.numel() + b.numel() - 1
-    nfft = 1 << (n - 1).bit_length()
-    ir = torch.fft.irfft(torch.fft.rfft(a, nfft) * torch.fft.rfft(b, nfft), nfft)[:n]
+    ir = _native.convolve_full(a, b)
     ir = ir - ir.mean()
     return ir / ir.abs().max()
 

@@ -1,6 +1,8 @@
 """GPU: the CUDA path (through the Python surface -> C ABI) against the reference's
 golden vectors and against the oracle on seeded inputs. Tolerance: BASELINE.json
 north_star, max|y - y_ref| <= 1e-4 * max|y_ref| per clip, fp32."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 import torch
@@ -469,3 +471,77 @@ def test_measure_model_ir_end_to_end(tmp_path):
     ref = P.deconvolve_direct(P.postprocess(y, 48000).reshape(-1).numpy(), inv)
     assert np.abs(ir[0].numpy().astype(np.float64) - ref).max() <= 5e-4
     assert (tmp_path / "IR_models" / "tcn_IR.wav").exists()
+
+
+# ---------------------------------------------------------------------------------------------- analysis kernels (8f)
+@pytest.mark.parametrize("B,T", [(1, 480000), (16, 30001), (3, 7), (64, 4096)])
+def test_eval_metrics_on_device_match_oracle(B, T):
+    """MAE / ESR / DC of eval.py:118-121 as one fused device reduction, against the CPU restatement."""
+    from oracle import eval_oracle as E
+    from neural_audio_spring_reverb_b200 import _native
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    t = torch.randn(B, 1, T, generator=g) * torch.linspace(0.01, 1.0, B).view(B, 1, 1)
+    p = t + 0.05 * torch.randn(B, 1, T, generator=g) + 0.01
+    got = _native.eval_metrics(p.to(DEV), t.to(DEV))
+    ref = E.eval_metrics(p, t)
+    for k in ref:
+        assert abs(got[k] - ref[k]) <= 1e-9 * max(1.0, abs(ref[k])), (k, got[k], ref[k])
+    # unaligned rows (odd T, row starts off 16 bytes) take the scalar path: same numbers
+    assert _native.eval_metrics(t.to(DEV), t.to(DEV)) == {"eval/mae": 0.0, "eval/esr": 0.0, "eval/dc": 0.0}
+
+
+def test_evaluate_model_loop_on_device():
+    """eval.py:96-146 with a caller-supplied loader: mean metrics + rtf, predictions scored without leaving the GPU."""
+    from oracle import eval_oracle as E
+    from neural_audio_spring_reverb_b200.eval import evaluate_model
+    cfg = O.CONFIGS["cfg1"]
+    sd = O.config_state("cfg1")
+    m = build_model(cfg, sd, DEV)
+    batches = [(O.make_input(4, 1, 9000) * (i + 1) * 0.3, O.make_input(4, 1, 9000).flip(-1)) for i in range(3)]
+    config = dict(cond_dim=2, c0=0.25, c1=0.75, sample_rate=48000)
+    got = evaluate_model(None, batches, model=m, config=config)
+    cond = torch.tensor([[0.25, 0.75]]).repeat(4, 1)
+    want = {"eval/mae": 0.0, "eval/esr": 0.0, "eval/dc": 0.0}
+    for dry, wet in batches:
+        pred = O.forward(sd, O.config_dilations(cfg), dry, cond)
+        sc = E.eval_metrics(pred, wet)
+        for k in want:
+            want[k] += sc[k] / len(batches)
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-4 * max(abs(want[k]), 1e-6), (k, got[k], want[k])
+    assert got["eval/rtf"] > 0
+    with pytest.raises(ValueError):
+        evaluate_model(None, None, model=m)
+
+
+def test_rt60_on_device_matches_reference_lines(tmp_path):
+    """tools/rt60.py:49-72: the device scan against values produced by the reference's own source lines."""
+    from oracle import eval_oracle as E
+    from neural_audio_spring_reverb_b200.tools.rt60 import rt60_of, measure_rt60
+    z = np.load(Path(__file__).resolve().parent / "golden" / "analysis" / "rt60_ref.npz")
+    for (seed, n, fs, rt, tz, decay), ref in zip(E.RT60_CASES, z["rt60"]):
+        h = E.synthetic_ir(seed, n, fs, rt, tz)
+        got = rt60_of(h, fs, decay, DEV)
+        want = E.rt60_fp64(h, fs, decay)
+        assert got["i_nz"] == want["i_nz"] and got["i_5db"] == want["i_5db"] and got["i_decay"] == want["i_decay"], (got, want)
+        assert abs(got["rt60"] - ref) <= 2.0 / fs, (got, ref)
+    assert rt60_of(np.zeros(5000, np.float32), 48000.0, 60.0, DEV)["rt60"] == 0.0
+    # the `rt60` action: wav in, seconds out (rt60.py:38-39 casts the samples to float32 as they are)
+    from scipy.io import wavfile
+    seed, n, fs, rt, tz, decay = E.RT60_CASES[0]
+    h = E.synthetic_ir(seed, n, fs, rt, tz)
+    wavfile.write(tmp_path / "ir.wav", int(fs), h)
+    import argparse
+    assert abs(measure_rt60(argparse.Namespace(input=str(tmp_path / "ir.wav"), device=DEV)) - z["rt60"][0]) <= 2.0 / fs
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (5, 1300), (1025, 1024), (4097, 777), (30000, 20011)])
+def test_direct_convolution_kernel_matches_numpy(n, m):
+    """scipy.signal.convolve(method="direct") of ir_model.py:138-140 as a hand-written fp64 kernel."""
+    from neural_audio_spring_reverb_b200 import _native
+    g = np.random.default_rng(n * 7 + m)
+    a, b = g.standard_normal(n), g.standard_normal(m)
+    got = _native.convolve_full(torch.from_numpy(a).to(DEV), torch.from_numpy(b).to(DEV)).cpu().numpy()
+    ref = np.convolve(a, b, mode="full")
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()) * max(n, m) ** 0.5
