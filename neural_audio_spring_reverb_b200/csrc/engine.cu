@@ -49,7 +49,19 @@ struct BlockState {
   uint16_t* wtoep = nullptr;                 // first block on the tensor cores (toep_pack_weights)
   int toep_kp = 0;
   float toep_inv_sw = 1.f, toep_inv_sr = 1.f;
+  // path 3: a block with more than kPassTaps taps runs as several launches of the ring kernel ("tap passes"): pass p
+  // convolves taps [tap0, tap0 + k) of the block (counted backwards from the newest sample) on the input read tap0 * d
+  // rows earlier, adds the partial plane the passes before it wrote and either hands the raw sums on or - the last
+  // one, which also carries the 1x1 residual - finishes the block
+  struct TapPass {
+    uint16_t* w = nullptr;   // ring_pack_weights of the pass, all channel groups
+    int k = 0, tap0 = 0;
+    float inv_sr = 1.f;
+  };
+  std::vector<TapPass> passes;
 };
+
+constexpr int kPassTaps = RB_MAX_SLOTS - 1;   // taps per pass: the ring's slots minus the residual slot
 
 }  // namespace
 
@@ -60,6 +72,8 @@ struct nasr_engine {
   std::vector<BlockState> blocks;
   std::vector<TcMapCache> tc_cache;   // per block: last TMA descriptors
   std::vector<RingMapCache> ring_cache;
+  std::vector<std::vector<RingMapCache>> pass_cache;   // [block][pass]
+  DevBuf partial;   // tap passes: fp32 conv sums [clips][T][32 * groups]
   ToepMapCache toep_cache;
   float* wout = nullptr;  // [out_ch][Cp]
   FoldArgs* fold_dev = nullptr;
@@ -232,6 +246,9 @@ void free_block(BlockState& b) {
   b.w0 = nullptr;
   if (b.wtoep) cudaFree(b.wtoep);
   b.wtoep = nullptr;
+  for (auto& q : b.passes)
+    if (q.w) cudaFree(q.w);
+  b.passes.clear();
 }
 
 // tc = false plans the all-fp32 chain (generic kernels, CL planes) for this call
@@ -291,9 +308,39 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
     t.inv_sw = bs.inv_sw * kActInv; t.inv_sr = bs.inv_sr * kActInv;   // the input plane holds value * kActScale
     t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_cur; t.prof = a.prof;
     err = launch_ring_block(L, s);
+  } else if (allow_tc && tc_chain && bs.path == 3) {
+    const int n_grp = ring_groups(e->desc.arch);
+    const int pin_ld = 32 * n_grp;
+    err = cudaSuccess;
+    for (size_t q = 0; q < bs.passes.size() && err == cudaSuccess; ++q) {
+      const BlockState::TapPass& ps = bs.passes[q];
+      const bool last = q + 1 == bs.passes.size();
+      RingLaunch L{};
+      L.cache = &e->pass_cache[i][q];
+      L.in = a.in; L.in_rows = a.in_rows; L.in_clip_stride_elems = a.in_clip_stride;
+      L.wpacked = ps.w; L.arch = e->desc.arch; L.sm_count = e->sm_count; L.pdl = e->pdl; L.acc = true;
+      RingArgs& t = L.a;
+      t.in_row0 = a.in_row0 - (long long)ps.tap0 * a.d;   // rows before the plane are the causal zero fill
+      t.B = a.B; t.T = a.T; t.k = ps.k; t.d = a.d;
+      t.scale = a.scale; t.shift = a.shift; t.ld_affine = bs.Wp; t.slope = a.slope;
+      t.inv_sw = bs.inv_sw * kActInv; t.inv_sr = ps.inv_sr * kActInv;
+      t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_cur; t.prof = a.prof;
+      t.pin = q > 0 ? (const float*)e->partial.p : nullptr;
+      t.pin_clip_stride = a.T * pin_ld; t.pin_ld = pin_ld;
+      if (last) {
+        t.out = a.out; t.out_fmt = a.out_fmt; t.out_clip_stride = a.out_clip_stride; t.out_rows = a.out_rows;
+        t.out_row0 = a.out_row0;
+      } else {
+        t.raw_out = 1;
+        t.out = e->partial.p; t.out_fmt = FMT_CL; t.out_clip_stride = a.T * pin_ld; t.out_rows = a.T; t.out_row0 = 0;
+        t.out_row_bytes = pin_ld * 4;
+      }
+      err = launch_ring_block(L, s);
+      if (err == cudaSuccess && !last) e->launches += 1;
+    }
   } else {
     err = cudaErrorNotSupported;
-    if (bs.wtoep && allow_tc && tc_chain && a.in_fmt == FMT_NCT && toep_eligible(a.arch, a.Cin, a.Cout, a.k, a.out_fmt)) {
+    if (bs.wtoep && allow_tc && tc_chain && a.in_fmt == FMT_NCT && toep_eligible(a.arch, a.Cin, a.Coutp, a.k, a.out_fmt)) {
       ToepLaunch L{};
       L.cache = &e->toep_cache; L.wpacked = bs.wtoep; L.arch = a.arch; L.sm_count = e->sm_count; L.Kp = bs.toep_kp;
       L.pdl = e->pdl;
@@ -306,7 +353,12 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
       t.sat_flag = e->sat_cur; t.prof = a.prof;
       err = launch_toep_block(L, s);
     }
-    if (err == cudaErrorNotSupported && bs.w0 && allow_tc) err = launch_first_block(a, bs.w0, e->sm_count, s);
+    if (err == cudaErrorNotSupported && bs.w0 && allow_tc) {
+      // w0 is laid out for the padded widths (channels 16 .. 31 of a lowered 16-channel net are zero columns)
+      BlockArgs a2 = a;
+      a2.Cout = a.Coutp; a2.W = a.Wp;
+      err = launch_first_block(a2, bs.w0, e->sm_count, s);
+    }
     if (err == cudaErrorNotSupported) err = launch_generic_block(a, e->sm_count, s);
   }
   if (err != cudaSuccess)
@@ -321,6 +373,12 @@ inline size_t plane_row_bytes(const nasr_engine* e) { return (size_t)e->Cp * 4; 
 // tail slack of every activation plane: the ring kernel's grouped TMA view may read (never use) rows past
 // the last clip (ring_block.cuh)
 inline size_t plane_slack_bytes() { return (size_t)RB_SLACK_ROWS * 128; }
+// fp32 plane of conv sums that the tap passes of a block hand to each other (0 when no block runs in passes)
+inline size_t partial_bytes(const nasr_engine* e, long long clips, long long T) {
+  for (const auto& b : e->blocks)
+    if (b.path == 3) return (size_t)clips * T * 128 * ring_groups(e->desc.arch) + plane_slack_bytes();
+  return 0;
+}
 // ping-pong activation planes of the one-shot forward (a split out_net needs a plane for the last block too)
 inline int planes_needed(const nasr_engine* e) {
   const int n = (int)e->blocks.size();
@@ -355,6 +413,7 @@ void nasr_engine_destroy(nasr_engine* e) {
     if (e->sat_host) cudaFreeHost((void*)e->sat_host);
     release(e->plane[0]); release(e->plane[1]);
     for (auto& p : e->splane) release(p);
+    release(e->partial);
     release(e->scratch); release(e->sfinal); release(e->hx); release(e->hy); release(e->hc); release(e->ychunk);
     for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (int q = 0; q < 2; ++q) {
@@ -398,6 +457,13 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
   e->sm_count = prop.multiProcessorCount;
   e->C = desc->n_channels;
   e->Cp = round_up(desc->n_channels, 4);
+  // 16 .. 31 channels (the shipped WaveNets, BASELINE config 1): planes and weights are padded to 32 channels with
+  // zeros, so that the blocks run on the 32-channel tensor-core kernels (NASR_LOWER=0: fp32 FFMA kernels as before)
+  {
+    const char* env = getenv("NASR_LOWER");
+    const bool lower = !(env && atoi(env) == 0);
+    if (lower && desc->path != NASR_PATH_FP32 && e->C >= 16 && e->C < 32) e->Cp = 32;
+  }
   if (const char* env = getenv("NASR_WORKSPACE_MB")) {
     const long long mb = atoll(env);
     if (mb > 0) e->budget_bytes = (size_t)mb << 20;
@@ -409,6 +475,7 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
   e->blocks.resize(n);
   e->tc_cache.resize(n);
   e->ring_cache.resize(n);
+  e->pass_cache.resize(n);
   if (const char* env = getenv("NASR_PDL")) e->pdl = atoi(env) != 0;
   if (const char* env = getenv("NASR_ZEROCOPY")) e->zero_copy = atoi(env) != 0;
   if (const char* env = getenv("NASR_HOST_PIPE")) e->host_pipe = atoi(env) != 0;
@@ -435,15 +502,28 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
     // kernel of block blk: 0 = fp32 FFMA, 1 = tcgen05 tap-gather (tc_block.cu), 2 = tcgen05 accumulator ring
     // (ring_block.cu; the GCN ring kernel splits the channels over two CTAs and cannot fuse out_net: that block
     // writes a channels-last fp32 plane and a small out_net kernel follows, BlockState::split_out)
+    // 3 = the ring kernel in tap passes (more taps than the ring has slots)
+    // dev: NASR_FORCE_PASSES=n runs every block with more than n taps in passes of n taps
+    int pass_taps = kPassTaps;
+    bool force_pass = false;
+    if (const char* env = getenv("NASR_FORCE_PASSES")) {
+      const int v = atoi(env);
+      if (v >= 1 && v <= kPassTaps) { pass_taps = v; force_pass = true; }
+    }
     auto path_of = [&](int blk) {
       if (desc->path == NASR_PATH_FP32 || blk < 1 || blk >= n) return 0;
-      if (desc->path == NASR_PATH_AUTO && ring_eligible(desc->arch, C, C, k, desc->dilations[blk])) return 2;
-      return tc_eligible(desc->arch, C, C, k) ? 1 : 0;
+      if (force_pass && desc->path == NASR_PATH_AUTO && k > pass_taps &&
+          ring_eligible(desc->arch, Cp, Cp, pass_taps, desc->dilations[blk])) return 3;
+      if (desc->path == NASR_PATH_AUTO && ring_eligible(desc->arch, Cp, Cp, k, desc->dilations[blk])) return 2;
+      if (tc_eligible(desc->arch, Cp, Cp, k)) return 1;
+      if (desc->path == NASR_PATH_AUTO && k > kPassTaps && ring_eligible(desc->arch, Cp, Cp, kPassTaps, desc->dilations[blk]))
+        return 3;
+      return 0;
     };
     b.path = path_of(i);
     b.in_fmt = (i == 0) ? FMT_NCT : (b.path != 0 ? FMT_SPLIT16 : FMT_CL);
     b.out_fmt = (i == n - 1) ? FMT_FINAL : (path_of(i + 1) != 0 ? FMT_SPLIT16 : FMT_CL);
-    b.split_out = gcn && i == n - 1 && b.path == 2;
+    b.split_out = gcn && i == n - 1 && (b.path == 2 || b.path == 3);
     if (b.split_out) b.out_fmt = FMT_CL;
     if (b.Wp / b.NC > 16) { rc = fail(nullptr, NASR_ERR_INVALID, "channel count too large for the generic kernel"); break; }
 
@@ -488,33 +568,70 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
       for (int ci = 0; ci < b.Cin; ++ci) h_wres[(size_t)ci * b.Coutp + co] = res_w[(size_t)co * b.Cin + ci];
 
     up(&b.wconv, h_wconv); up(&b.wres, h_wres); up(&b.bias, h_bias); up(&b.perm, perm);
+    // the tensor-core packers and the first-block kernel take the weights in the original layout at the PADDED widths:
+    // conv [Wp][Cinp][k] (GCN: [tanh Cp | sigmoid Cp]), residual [Cp][Cinp]; identical to the blob when C == Cp
+    std::vector<float> p_conv((size_t)b.Wp * b.Cinp * k, 0.f), p_res((size_t)Cp * b.Cinp, 0.f);
+    for (int co = 0; co < b.W; ++co)
+      for (int ci = 0; ci < b.Cin; ++ci)
+        for (int j = 0; j < k; ++j)
+          p_conv[((size_t)perm[co] * b.Cinp + ci) * k + j] = conv_w[((size_t)co * b.Cin + ci) * k + j];
+    for (int co = 0; co < C; ++co)
+      for (int ci = 0; ci < b.Cin; ++ci) p_res[(size_t)co * b.Cinp + ci] = res_w[(size_t)co * b.Cin + ci];
     if (i == 0 && b.Cin <= 4) {
-      std::vector<float> h_w0((size_t)k * b.Cin * b.W);
+      std::vector<float> h_w0((size_t)k * b.Cin * b.Wp, 0.f);
       for (int co = 0; co < b.W; ++co)
         for (int ci = 0; ci < b.Cin; ++ci)
-          for (int j = 0; j < k; ++j) h_w0[((size_t)j * b.Cin + ci) * b.W + co] = conv_w[((size_t)co * b.Cin + ci) * k + j];
+          for (int j = 0; j < k; ++j) h_w0[((size_t)j * b.Cin + ci) * b.Wp + perm[co]] = conv_w[((size_t)co * b.Cin + ci) * k + j];
       up(&b.w0, h_w0);
-      if (desc->path != NASR_PATH_FP32 && toep_eligible(desc->arch, b.Cin, C, k, FMT_SPLIT16)) {
+      if (desc->path != NASR_PATH_FP32 && toep_eligible(desc->arch, b.Cin, Cp, k, FMT_SPLIT16)) {
         std::vector<uint16_t> h_wt;
-        toep_pack_weights(desc->arch, b.Cin, k, conv_w, res_w, h_wt, &b.toep_inv_sw, &b.toep_inv_sr, &b.toep_kp);
+        toep_pack_weights(desc->arch, b.Cin, k, p_conv.data(), p_res.data(), h_wt, &b.toep_inv_sw, &b.toep_inv_sr, &b.toep_kp);
         up(&b.wtoep, h_wt);
       }
     }
     if (b.path == 1) {
       std::vector<uint16_t> h_wtc;
-      tc_pack_weights(desc->arch, k, conv_w, res_w, h_wtc, &b.inv_sw, &b.inv_sr);
+      tc_pack_weights(desc->arch, k, p_conv.data(), p_res.data(), h_wtc, &b.inv_sw, &b.inv_sr);
       up(&b.wtc, h_wtc);
     } else if (b.path == 2) {
       std::vector<uint16_t> h_wtc, part;
       for (int g = 0; g < ring_groups(desc->arch); ++g) {
-        ring_pack_weights(desc->arch, g, k, conv_w, res_w, part, &b.inv_sw, &b.inv_sr);
+        ring_pack_weights(desc->arch, g, k, p_conv.data(), p_res.data(), part, &b.inv_sw, &b.inv_sr);
         h_wtc.insert(h_wtc.end(), part.begin(), part.end());
       }
       up(&b.wtc, h_wtc);
-      if (tc_eligible(desc->arch, C, C, k) && !b.split_out) {
+      if (tc_eligible(desc->arch, Cp, Cp, k) && !b.split_out) {
         std::vector<uint16_t> h_wtg;
-        tc_pack_weights(desc->arch, k, conv_w, res_w, h_wtg, &b.g_inv_sw, &b.g_inv_sr);
+        tc_pack_weights(desc->arch, k, p_conv.data(), p_res.data(), h_wtg, &b.g_inv_sw, &b.g_inv_sr);
         up(&b.wtg, h_wtg);
+      }
+    } else if (b.path == 3) {
+      // tap passes: pass p takes the taps s in [15 p, 15 p + kp) counted backwards (V_s = W[:, :, k-1-s]), i.e. the
+      // kernel positions j in [k - 15 p - kp, k - 15 p); one weight scale for the whole block.  They run oldest taps
+      // first: the pass of the newest taps reads the input unshifted, so the 1x1 residual (x[t] itself) rides on it
+      // and it finishes the block
+      const float sw = ring_weight_scale(p_conv.data(), p_conv.size());
+      const std::vector<float> zero_res((size_t)Cp * b.Cinp, 0.f);
+      const int np = (k + pass_taps - 1) / pass_taps;
+      e->pass_cache[i].resize(np);
+      for (int q = 0; q < np; ++q) {
+        BlockState::TapPass ps;
+        ps.tap0 = (np - 1 - q) * pass_taps;
+        ps.k = k - ps.tap0 < pass_taps ? k - ps.tap0 : pass_taps;
+        const int j0 = k - ps.tap0 - ps.k;
+        std::vector<float> sub((size_t)b.Wp * b.Cinp * ps.k);
+        for (size_t r = 0; r < (size_t)b.Wp * b.Cinp; ++r)
+          for (int j = 0; j < ps.k; ++j) sub[r * ps.k + j] = p_conv[r * k + j0 + j];
+        const bool last = q == np - 1;
+        std::vector<uint16_t> h_w, part;
+        for (int g = 0; g < ring_groups(desc->arch); ++g) {
+          float isw = 1.f;
+          ring_pack_weights(desc->arch, g, ps.k, sub.data(), last ? p_res.data() : zero_res.data(), part, &isw, &ps.inv_sr, sw);
+          b.inv_sw = isw;
+          h_w.insert(h_w.end(), part.begin(), part.end());
+        }
+        up(&ps.w, h_w);
+        b.passes.push_back(ps);
       }
     }
     if (desc->has_film) {
@@ -678,6 +795,11 @@ static int ensure_planes(nasr_engine* e, int want, int64_t T, cudaStream_t s, in
         NASR_CUDA(e, ensure(e->plane[q], per_clip * *slice + plane_slack_bytes()));
       }
     }
+  }
+  const size_t need_partial = partial_bytes(e, *slice, T);
+  if (e->partial.cap < need_partial) {
+    NASR_CUDA(e, cudaStreamSynchronize(s));
+    NASR_CUDA(e, ensure(e->partial, need_partial));
   }
   return NASR_OK;
 }
@@ -1118,12 +1240,14 @@ int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev, int B, 
       need_scratch += (segs * bs.hist * ((i == 0) ? 4 : (size_t)rb) + 15) & ~(size_t)15;
     }
     const size_t need_y = (size_t)B * e->desc.out_ch * Tc * sizeof(float);
-    if (e->sfinal.cap < need_final || e->scratch.cap < need_scratch || e->ychunk.cap < need_y) {
+    const size_t need_partial = partial_bytes(e, B, Tc);
+    if (e->sfinal.cap < need_final || e->scratch.cap < need_scratch || e->ychunk.cap < need_y || e->partial.cap < need_partial) {
       NASR_CUDA(e, cudaStreamSynchronize(s));
       drop_chunk_graphs(e);
       NASR_CUDA(e, ensure(e->sfinal, need_final));
       NASR_CUDA(e, ensure(e->scratch, need_scratch));
       NASR_CUDA(e, ensure(e->ychunk, need_y));
+      NASR_CUDA(e, ensure(e->partial, need_partial));
     }
   }
   sat_stream(e);

@@ -157,7 +157,9 @@ struct Span {
 
 }  // namespace
 
-template <int ARCH>
+// ACC: the tap-pass variant (RingArgs::pin / raw_out); a separate instantiation so that the extra registers of the
+// partial-sum rows never touch the plain kernel
+template <int ARCH, bool ACC>
 __global__ void __launch_bounds__((4 * RB_ESETS + 2) * 32, 1)
 ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map,
                   const __grid_constant__ CUtensorMap out_map, const RingArgs a) {
@@ -525,6 +527,50 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         const bool zero_c = (a.dbg & 256) || i + 1 < s.nsteps;
         const bool zero_r = (a.dbg & 256) || (s.nsteps - 2 - i >= km1);
         uint64_t* drained_e = &drained[e & 1u];
+        // tap passes: this row's conv sums of the earlier passes (issued before the wait: the address is known)
+        uint4 pv[ACC ? 8 : 1];
+        if (ACC && a.pin) {
+          const long long t = t0 + off;
+          if (ok && t < a.T) {
+            const uint4* pp = reinterpret_cast<const uint4*>(a.pin + (long long)s.b * a.pin_clip_stride + t * a.pin_ld + grp * 32);
+#pragma unroll
+            for (int q = 0; q < (ACC ? 8 : 1); ++q)
+              asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pv[q].x), "=r"(pv[q].y), "=r"(pv[q].z), "=r"(pv[q].w) : "l"(pp + q) : "memory");
+          } else {
+#pragma unroll
+            for (int q = 0; q < (ACC ? 8 : 1); ++q) pv[q] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        auto add_pin = [&](uint32_t (&u)[32]) {
+          if (ACC && a.pin) {
+#pragma unroll
+            for (int q = 0; q < (ACC ? 8 : 1); ++q) {
+              u[4 * q] = __float_as_uint(__uint_as_float(u[4 * q]) + __uint_as_float(pv[q].x));
+              u[4 * q + 1] = __float_as_uint(__uint_as_float(u[4 * q + 1]) + __uint_as_float(pv[q].y));
+              u[4 * q + 2] = __float_as_uint(__uint_as_float(u[4 * q + 2]) + __uint_as_float(pv[q].z));
+              u[4 * q + 3] = __float_as_uint(__uint_as_float(u[4 * q + 3]) + __uint_as_float(pv[q].w));
+            }
+          }
+        };
+        // coalesced stores of the staged rows: NCH lanes per row, chunk my_c of the row at byte cb
+        auto store_rows = [&](int cb) {
+#pragma unroll
+          for (int q = 0; q < NCH; ++q) {
+            const int rl = RPI * q + my_r;       // row within the warp's 32
+            const int rsw = (NCH == 8) ? (rl & 7) : ((rl >> 1) & 3);
+            const uint4 val = *reinterpret_cast<const uint4*>(stage + rl * (NCH * 16) + ((my_c ^ rsw) * 16));
+            const long long t = t0 + offq[q];
+            if (((okm >> q) & 1u) && t < a.T && !(a.dbg & 16)) {   // dbg 16 (dev): everything but the global stores
+              uint4* gp = reinterpret_cast<uint4*>(out_clip + (a.out_row0 + t) * (long long)a.out_row_bytes + cb);
+              if (a.dbg & 32)
+                asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+              else if (a.dbg & 64)
+                asm volatile("st.global.wt.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+              else
+                *gp = val;
+            } else if ((a.dbg & 16) && val.x == 0x12345678u) *a.sat_flag = 2u;
+          }
+        };
         mbar_wait(&done[e % NDONE], (e / NDONE) & 1u);
         tc_fence_after();
         if (e == 0 && threadIdx.x == 0) rb_stamp(a, 7);
@@ -595,8 +641,14 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(drained_e);
           if (quad == 0 && lane == 0 && sp == sp0) rb_step_stamp(a, 1, i + km1);
+          add_pin(u);
           // 4 channels: affine -> PReLU -> + residual
           auto out4 = [&](int c, float (&o4)[4]) {
+            if (ACC && a.raw_out) {   // tap pass that is not the block's last: hand the raw conv sums on
+              o4[0] = __uint_as_float(u[c]); o4[1] = __uint_as_float(u[c + 1]);
+              o4[2] = __uint_as_float(u[c + 2]); o4[3] = __uint_as_float(u[c + 3]);
+              return;
+            }
             const float4 s4 = *reinterpret_cast<const float4*>(aff + c);
             const float4 h4 = *reinterpret_cast<const float4*>(aff + 32 + c);
             const float2 y0 = __ffma2_rn(make_float2(__uint_as_float(u[c]), __uint_as_float(u[c + 1])), make_float2(s4.x, s4.y),
@@ -658,6 +710,20 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(drained_e);
           if (a.out_fmt == FMT_FINAL) continue;   // not produced by the GCN groups (engine: split out_net)
+          add_pin(u);
+          if (ACC && a.raw_out) {   // raw conv sums of this group: 32 floats = two staged rounds of 16
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              float o[16];
+#pragma unroll
+              for (int c = 0; c < 16; ++c) o[c] = __uint_as_float(u[16 * r + c]);
+              stage16(o, 0, 2);
+              __syncwarp();
+              store_rows(grp * 128 + r * 64 + my_c * 16);
+              __syncwarp();
+            }
+            continue;
+          }
           float o[16];
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
@@ -686,22 +752,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         }
         __syncwarp();
         // ---- coalesced stores: 8 (4) lanes per row ----
-#pragma unroll
-        for (int q = 0; q < NCH; ++q) {
-          const int rl = RPI * q + my_r;       // row within the warp's 32
-          const int rsw = (NCH == 8) ? (rl & 7) : ((rl >> 1) & 3);
-          const uint4 val = *reinterpret_cast<const uint4*>(stage + rl * (NCH * 16) + ((my_c ^ rsw) * 16));
-          const long long t = t0 + offq[q];
-          if (((okm >> q) & 1u) && t < a.T && !(a.dbg & 16)) {   // dbg 16 (dev): everything but the global stores
-            uint4* gp = reinterpret_cast<uint4*>(out_clip + (a.out_row0 + t) * 128LL + cbyte);
-            if (a.dbg & 32)
-              asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
-            else if (a.dbg & 64)
-              asm volatile("st.global.wt.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
-            else
-              *gp = val;
-          } else if ((a.dbg & 16) && val.x == 0x12345678u) *a.sat_flag = 2u;
-        }
+        store_rows(cbyte);
         if (quad == 0 && lane == 0 && sp == sp0) rb_step_stamp(a, 2, i + km1);
         __syncwarp();
       }
@@ -743,19 +794,22 @@ bool ring_eligible(int arch, int Cin, int C, int k, int d) {
 //                 channels 16g.., rows 16..31 = sigmoid channels 32 + 16g..)
 //   block k     : residual 1x1 (GCN: rows 0..15 = output channels 16g.., rows 16..31 zero)
 // each row = 32 x fp16 hi(w * S) then 32 x fp16 lo(w * S); S = power of two with max|w| * S in [512, 1024).
+// power of two S with max|w| * S in [512, 1024)
+float ring_weight_scale(const float* w, size_t n) {
+  float mx = 0.f;
+  for (size_t i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(w[i]));
+  if (!(mx > 0.f) || !isfinite(mx)) return 1.0f;
+  int e;
+  frexpf(mx, &e);
+  return ldexpf(1.0f, 10 - e);
+}
+
 void ring_pack_weights(int arch, int grp, int k, const float* conv_w /*[W][32][k]*/, const float* res_w /*[32][32]*/,
-                       std::vector<uint16_t>& out, float* inv_sw, float* inv_sr) {
+                       std::vector<uint16_t>& out, float* inv_sw, float* inv_sr, float force_sw, float force_sr) {
   const int W = arch == 1 ? 64 : 32, C = 32, NS = k + 1;
   out.assign((size_t)NS * 32 * 64, 0);
-  auto pow2_scale = [](const float* w, size_t n) {
-    float mx = 0.f;
-    for (size_t i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(w[i]));
-    if (!(mx > 0.f) || !isfinite(mx)) return 1.0f;
-    int e;
-    frexpf(mx, &e);
-    return ldexpf(1.0f, 10 - e);
-  };
-  const float sw = pow2_scale(conv_w, (size_t)W * C * k), sr = pow2_scale(res_w, (size_t)C * C);
+  const float sw = force_sw > 0.f ? force_sw : ring_weight_scale(conv_w, (size_t)W * C * k);
+  const float sr = force_sr > 0.f ? force_sr : ring_weight_scale(res_w, (size_t)C * C);
   *inv_sw = 1.0f / sw;
   *inv_sr = 1.0f / sr;
   auto put = [&](int block, int row, int ci, float v) {
@@ -826,7 +880,8 @@ cudaError_t ring_plan(int arch, int sm_count, long long cached_n, RingArgs& a, l
   const long long ctas = sm_count / n_grp > 0 ? sm_count / n_grp : 1;   // span walkers per group
   long long n_max = 512;
   if (a.mode == 0) {
-    const long long cap = (RB_SLACK_ROWS - (long long)(a.k + 1) * a.d - a.in_row0) / a.d;   // over-read bound
+    // over-read bound (a tap pass reads with in_row0 < 0: rows before the plane are the causal zero fill)
+    const long long cap = (RB_SLACK_ROWS - (long long)(a.k + 1) * a.d - (a.in_row0 > 0 ? a.in_row0 : 0)) / a.d;
     if (cap < 1) return cudaErrorInvalidConfiguration;
     if (n_max > cap) n_max = cap;
   }
@@ -863,7 +918,7 @@ int ring_debug_plan(int arch, int k, int d, int B, long long T, long long in_row
   if (B <= 0 || T <= 0 || ring_plan(arch, sm_count, 0, a, &grid) != cudaSuccess) return 1;
   const long long v[16] = {a.mode, a.G, a.L, a.n, a.S, a.NP, a.spans_per_strip, a.total_spans, grid, a.stages, a.NS, a.NW,
                            a.tmem_cols, (long long)rb_smem_bytes(a.NS, a.stages), a.n_grp,
-                           a.mode == 0 ? a.in_row0 + a.S + a.d : 0};
+                           a.mode == 0 ? (a.in_row0 > 0 ? a.in_row0 : 0) + a.S + a.d : 0};
   for (int i = 0; i < 16; ++i) out16[i] = v[i];
   return 0;
 }
@@ -890,6 +945,8 @@ int ring_debug_steps(unsigned long long* host) {
 cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   RingArgs a = L.a;
   if (a.B <= 0 || a.T <= 0) return cudaSuccess;
+  if (a.out_row_bytes <= 0) a.out_row_bytes = 128;
+  if (!L.acc && (a.pin || a.raw_out)) return cudaErrorInvalidValue;
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("NASR_RB_DBG"); dbg = e ? atoi(e) : 0; }
@@ -932,7 +989,7 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
     if (a.mode == 0) {
       // dims (channel pair, r, j, clip): row (r, j) = j * S + r.  r spans the history prefix plus one group
       // stride; j spans the clip.  The last group may run up to S + in_row0 rows past the clip (RB_SLACK_ROWS).
-      const uint64_t rext = (uint64_t)(a.in_row0 + a.S + a.d);
+      const uint64_t rext = (uint64_t)((a.in_row0 > 0 ? a.in_row0 : 0) + a.S + a.d);
       const uint64_t jext = (uint64_t)((L.in_rows + a.S - 1) / a.S);
       ok = make_group_map(&in_map, L.in, rext, jext, (uint64_t)a.B, (uint64_t)a.S, (uint64_t)L.in_clip_stride_elems,
                           (uint32_t)a.d, (uint32_t)a.G);
@@ -949,7 +1006,7 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
     static int tma_env = -1;
     if (tma_env < 0) { const char* ev = getenv("NASR_TMA_STORE"); tma_env = ev ? atoi(ev) : 1; }
     const bool pow2 = (a.d & (a.d - 1)) == 0;
-    a.tma_out = tma_env && L.arch == 0 && (a.out_fmt == FMT_SPLIT16 || a.out_fmt == FMT_CL) &&
+    a.tma_out = tma_env && L.arch == 0 && (a.out_fmt == FMT_SPLIT16 || a.out_fmt == FMT_CL) && a.out_row_bytes == 128 &&
                 (a.mode == 1 || (pow2 && a.d <= 64)) ? 1 : 0;
     if (a.tma_out) {
       const long long stride16 = a.out_clip_stride * (a.out_fmt == FMT_SPLIT16 ? 1 : 2);   // 16-bit elements between clips
@@ -976,9 +1033,10 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   }
 
   cudaError_t err;
-  static unsigned long long attr_set[2] = {0, 0};
-  const void* fn = L.arch == 0 ? (const void*)ring_block_kernel<0> : (const void*)ring_block_kernel<1>;
-  if (attr_needed_on_this_device(attr_set[L.arch])) {
+  static unsigned long long attr_set[4] = {0, 0, 0, 0};
+  const void* fn = L.arch == 0 ? (L.acc ? (const void*)ring_block_kernel<0, true> : (const void*)ring_block_kernel<0, false>)
+                               : (L.acc ? (const void*)ring_block_kernel<1, true> : (const void*)ring_block_kernel<1, false>);
+  if (attr_needed_on_this_device(attr_set[L.arch + (L.acc ? 2 : 0)])) {
     err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (err != cudaSuccess) return err;
   }
@@ -992,8 +1050,10 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = L.pdl ? 1 : 0;
-  if (L.arch == 0) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<0>, in_map, w_map, out_map, a);
-  else err = cudaLaunchKernelEx(&cfg, ring_block_kernel<1>, in_map, w_map, out_map, a);
+  if (L.arch == 0 && !L.acc) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<0, false>, in_map, w_map, out_map, a);
+  else if (L.arch == 0) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<0, true>, in_map, w_map, out_map, a);
+  else if (!L.acc) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<1, false>, in_map, w_map, out_map, a);
+  else err = cudaLaunchKernelEx(&cfg, ring_block_kernel<1, true>, in_map, w_map, out_map, a);
   if (err != cudaSuccess) return err;
   return cudaGetLastError();
 }

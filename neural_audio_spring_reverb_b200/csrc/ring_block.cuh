@@ -41,6 +41,13 @@ struct RingArgs {
   int out_ch, final_tanh;
   unsigned int* sat_flag;
   int tma_out;             // rows leave through TMA stores of the staging tiles where the geometry allows
+  // tap passes (k > 15, engine.cu): a block's taps are split over several launches of this kernel that hand the conv
+  // sums on through an fp32 plane [B][T][pin_ld] (32 floats per channel group: the raw accumulator columns)
+  const float* pin;        // partial sums of the earlier passes, added to the conv accumulators, or NULL
+  long long pin_clip_stride;   // floats between clips
+  int pin_ld;              // floats per row (32 * n_grp)
+  int raw_out;             // 1: write the raw conv sums (+ pin) to `out` (same layout as pin) instead of the block's output
+  int out_row_bytes;       // bytes per output plane row (0 = 128)
   int l2_prefetch;         // > 0: TMA-prefetch the input tile of that many steps ahead into L2
   unsigned long long* prof;      // nasr_forward_profiled: {start, end} stamps of this launch, or NULL
   unsigned long long* dbg_buf;   // dev only: per-CTA timeline stamps
@@ -71,6 +78,7 @@ struct RingLaunch {
   const void* wpacked;              // device buffer from ring_pack_weights (one group)
   int arch, sm_count;
   bool pdl = false;                 // programmatic dependent launch (prologue overlaps the previous kernel's tail)
+  bool acc = false;                 // tap-pass variant of the kernel (a.pin / a.raw_out honoured)
   RingArgs a;
 };
 
@@ -79,8 +87,11 @@ struct RingLaunch {
 bool ring_eligible(int arch, int Cin, int C, int k, int d);
 // number of weight groups (launches per block): 1 for TCN, 2 for GCN
 int ring_groups(int arch);
+// force_sw / force_sr > 0: use these power-of-two weight scales instead of deriving them from the arrays (tap passes
+// of one block must share them)
 void ring_pack_weights(int arch, int grp, int k, const float* conv_w, const float* res_w, std::vector<uint16_t>& out,
-                       float* inv_sw, float* inv_sr);
+                       float* inv_sw, float* inv_sr, float force_sw = 0.f, float force_sr = 0.f);
+float ring_weight_scale(const float* w, size_t n);
 cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s);
 int ring_debug_stamps(unsigned long long* host, int max_ctas);
 int ring_debug_steps(unsigned long long* host);

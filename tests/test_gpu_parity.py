@@ -418,6 +418,53 @@ def test_tensor_core_path_shapes(arch, n_blocks, k, g, mode, monkeypatch):
     assert m.saturated() is False
 
 
+PASS_SHAPES = [
+    # arch, n_blocks, C, k, growth: more taps than the ring kernel has accumulator slots (and than the tap-gather kernel can
+    # keep resident) -> the block runs as tap passes of the ring kernel (engine.cu path 3); the shipped k = 99 shapes
+    ("TCN", 2, 32, 99, 14), ("GCN", 2, 32, 99, 512), ("GCN", 3, 16, 99, 10),
+    # pass boundaries: exactly three full passes, a last pass of one tap, both walk modes, a middle block
+    ("TCN", 3, 32, 45, 3), ("TCN", 3, 32, 46, 128), ("GCN", 3, 32, 20, 5),
+]
+
+
+@pytest.mark.parametrize("arch,n_blocks,C,k,g", PASS_SHAPES)
+def test_tap_pass_shapes(arch, n_blocks, C, k, g):
+    """k > 15 blocks on the tensor cores: several launches of the ring kernel that hand fp32 conv sums on (and, C = 16,
+    planes padded to 32 channels), against the oracle, one-shot and streamed in ragged chunks."""
+    import neural_audio_spring_reverb_b200 as N
+    cfg = dict(arch=arch, n_blocks=n_blocks, n_channels=C, kernel_size=k, dilation_growth=g, cond_dim=2)
+    sd = O.build_state(arch, n_blocks, C, k, 2, seed=k + g)
+    dil = [g ** i for i in range(n_blocks)]
+    m = build_model(cfg, sd, DEV)
+    assert [m._engine().block_path(i) for i in range(n_blocks)] == [0] + [3] * (n_blocks - 1)
+    rf = O.receptive_field(k, dil)
+    T = min(max(2 * rf, 9000), 70000) + 37
+    x = O.make_input(2, 1, T)
+    cond = torch.tensor([[0.2, 0.9], [0.7, 0.1]])
+    ref = O.forward(sd, dil, x, cond)
+    y = m(x.to(DEV), cond.to(DEV))
+    assert rel_err(y, ref) <= REL_TOL
+    st = N.CachedStream(m)
+    outs, s0 = [], 0
+    for n in (1, 130, 4099, 777, 10**9):
+        if s0 >= T:
+            break
+        outs.append(st(x[..., s0:s0 + n].to(DEV), cond.to(DEV)))
+        s0 += n
+    assert rel_err(torch.cat(outs, -1), ref) <= REL_TOL
+    assert m.saturated() is False
+
+
+def test_sixteen_channel_nets_run_on_the_tensor_core_kernels():
+    """16 <= C < 32 (BASELINE config 1, the shipped WaveNets): planes padded to 32 channels, blocks 1.. on the ring kernel."""
+    cfg = O.CONFIGS["cfg1"]
+    m = build_model(cfg, O.config_state("cfg1"), DEV)
+    assert [m._engine().block_path(i) for i in range(cfg["n_blocks"])] == [0, 2, 2, 2]
+    meta, y_ref, sd = load_golden("ckpt_WaveNet_egfxset_20240229_010530_48kHz")
+    m = build_model(meta["cfg"], sd, DEV)
+    assert all(m._engine().block_path(i) == 2 for i in range(1, len(meta["dilations"])))
+
+
 def test_batch_slicing_under_small_workspace(monkeypatch):
     """NASR_WORKSPACE_MB bounds the activation planes: the batch is then processed in slices."""
     monkeypatch.setenv("NASR_WORKSPACE_MB", "8")
