@@ -300,7 +300,7 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
     RingLaunch L{};
     L.cache = &e->ring_cache[i];
     L.in = a.in; L.in_rows = a.in_rows; L.in_clip_stride_elems = a.in_clip_stride;
-    L.wpacked = bs.wtc; L.arch = e->desc.arch; L.sm_count = e->sm_count; L.pdl = e->pdl;
+    L.wpacked = bs.wtc; L.arch = e->desc.arch; L.sm_count = e->sm_count; L.pdl = e->pdl; L.cin = e->Cp;
     RingArgs& t = L.a;
     t.out = a.out; t.out_fmt = a.out_fmt; t.out_clip_stride = a.out_clip_stride; t.out_rows = a.out_rows;
     t.out_row0 = a.out_row0; t.in_row0 = a.in_row0; t.B = a.B; t.T = a.T; t.k = a.k; t.d = a.d;
@@ -372,11 +372,11 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
 inline size_t plane_row_bytes(const nasr_engine* e) { return (size_t)e->Cp * 4; }
 // tail slack of every activation plane: the ring kernel's grouped TMA view may read (never use) rows past
 // the last clip (ring_block.cuh)
-inline size_t plane_slack_bytes() { return (size_t)RB_SLACK_ROWS * 128; }
+inline size_t plane_slack_bytes(const nasr_engine* e) { return (size_t)RB_SLACK_ROWS * (e->Cp > 32 ? e->Cp * 4 : 128); }
 // fp32 plane of conv sums that the tap passes of a block hand to each other (0 when no block runs in passes)
 inline size_t partial_bytes(const nasr_engine* e, long long clips, long long T) {
   for (const auto& b : e->blocks)
-    if (b.path == 3) return (size_t)clips * T * 128 * ring_groups(e->desc.arch) + plane_slack_bytes();
+    if (b.path == 3) return (size_t)clips * T * 128 * ring_groups(e->desc.arch) + plane_slack_bytes(e);
   return 0;
 }
 // ping-pong activation planes of the one-shot forward (a split out_net needs a plane for the last block too)
@@ -595,8 +595,8 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
       up(&b.wtc, h_wtc);
     } else if (b.path == 2) {
       std::vector<uint16_t> h_wtc, part;
-      for (int g = 0; g < ring_groups(desc->arch); ++g) {
-        ring_pack_weights(desc->arch, g, k, p_conv.data(), p_res.data(), part, &b.inv_sw, &b.inv_sr);
+      for (int g = 0; g < ring_groups(desc->arch, Cp); ++g) {
+        ring_pack_weights(desc->arch, g, k, p_conv.data(), p_res.data(), part, &b.inv_sw, &b.inv_sr, 0.f, 0.f, Cp);
         h_wtc.insert(h_wtc.end(), part.begin(), part.end());
       }
       up(&b.wtc, h_wtc);
@@ -790,9 +790,9 @@ static int ensure_planes(nasr_engine* e, int want, int64_t T, cudaStream_t s, in
       *slice = (int)fit;
     }
     for (int q = 0; q < nplanes; ++q) {
-      if (e->plane[q].cap < per_clip * *slice + plane_slack_bytes()) {
+      if (e->plane[q].cap < per_clip * *slice + plane_slack_bytes(e)) {
         NASR_CUDA(e, cudaStreamSynchronize(s));
-        NASR_CUDA(e, ensure(e->plane[q], per_clip * *slice + plane_slack_bytes()));
+        NASR_CUDA(e, ensure(e->plane[q], per_clip * *slice + plane_slack_bytes(e)));
       }
     }
   }
@@ -1071,7 +1071,7 @@ int nasr_forward_host(nasr_engine* e, const float* x_host, const float* cond_hos
 static size_t splane_bytes(const nasr_engine* e, int i, int B, long long Tcap) {
   const BlockState& b = e->blocks[i];
   if (i == 0) return (size_t)B * e->desc.in_ch * (b.hist + Tcap) * sizeof(float);
-  return (size_t)B * (b.hist + Tcap) * plane_row_bytes(e) + plane_slack_bytes();
+  return (size_t)B * (b.hist + Tcap) * plane_row_bytes(e) + plane_slack_bytes(e);
 }
 
 static int stream_alloc(nasr_engine* e, int B, long long Tcap, cudaStream_t s, bool keep_history) {
@@ -1232,7 +1232,7 @@ int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev, int B, 
   // engine-owned buffers the chunk's kernels use besides the planes (growing them invalidates captured graphs)
   {
     size_t need_final = 0, need_scratch = 0;
-    if (e->blocks[n - 1].split_out) need_final = (size_t)B * Tc * rb + plane_slack_bytes();
+    if (e->blocks[n - 1].split_out) need_final = (size_t)B * Tc * rb + plane_slack_bytes(e);
     for (int i = 0; i < n; ++i) {
       const BlockState& bs = e->blocks[i];
       if (bs.hist == 0 || Tc >= bs.hist) continue;

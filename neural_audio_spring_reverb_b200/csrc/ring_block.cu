@@ -159,7 +159,10 @@ struct Span {
 
 // ACC: the tap-pass variant (RingArgs::pin / raw_out); a separate instantiation so that the extra registers of the
 // partial-sum rows never touch the plain kernel
-template <int ARCH, bool ACC>
+// CIN: input (= output) channels of the block, 32 or 64.  64 (the shipped GCN-3 / GCN-springset shape): a plane row is
+// 256 bytes = [hi 64 ch | lo 64 ch], an input tile two SWIZZLE_128B sub-tiles of 16 KB (hi rows, lo rows), a product
+// term four 16-channel slices, a weight block two 4 KB sub-tiles; the 64 gate channels are four CTA groups of 16.
+template <int ARCH, bool ACC, int CIN>
 __global__ void __launch_bounds__((4 * RB_ESETS + 2) * 32, 1)
 ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map,
                   const __grid_constant__ CUtensorMap out_map, const RingArgs a) {
@@ -167,12 +170,16 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
   constexpr int EPI_WARPS = 4 * ESETS, PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
   constexpr int NO = (ARCH == 1) ? 16 : 32;   // output channels per thread row
   constexpr uint32_t NDONE = 2 * ESETS;
+  constexpr int TILE = CIN * 512;             // bytes of one input tile: 128 rows x CIN x (hi + lo) fp16
+  constexpr int WBLK = CIN * 128;             // bytes of one weight block: 32 rows x CIN x (hi + lo) fp16
+  constexpr int KS = CIN / 16;                // 16-channel slices per operand half
+  constexpr int NT = 3 * KS;                  // product terms per chunk: xh*wh, xh*wl, xl*wh per slice
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;                                            // stages x 16 KB input tiles
-  uint8_t* wsm = ring + (size_t)a.stages * RB_TILE_BYTES;           // NW x 4 KB stacked weights (wrapping copy: a chunk never wraps)
-  uint8_t* estage = wsm + (size_t)a.NW * 4096;                      // per epilogue warp: 4 KB row staging
+  uint8_t* wsm = ring + (size_t)a.stages * TILE;                    // NW stacked weight blocks (wrapping copy: a chunk never wraps)
+  uint8_t* estage = wsm + (size_t)a.NW * WBLK;                      // per epilogue warp: 4 KB row staging
   uint8_t* eaff = estage + (size_t)EPI_WARPS * 4096;                // per epilogue warp: 64 floats scale/shift
   uint64_t* bars = (uint64_t*)(eaff + (size_t)EPI_WARPS * 256);
   uint64_t* full = bars;                       // [RB_MAX_STAGES]
@@ -221,13 +228,17 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     // ================================ TMA producer ================================
     if (rb_elect_one()) {
       prefetch_tensormap(&in_map);
-      mbar_arrive_expect_tx(wfull, (uint32_t)(a.NW * 4096));
-      for (int p = 0; p < a.NW; ++p)
-        tma_load_3d(wsm + (size_t)p * 4096, &w_map, wfull, 0, (grp * NS + (p >= NS ? p - NS : p)) * 32, 0);
+      mbar_arrive_expect_tx(wfull, (uint32_t)(a.NW * WBLK));
+      for (int p = 0; p < a.NW; ++p) {
+        const int wrow = (grp * NS + (p >= NS ? p - NS : p)) * 32;
+        tma_load_3d(wsm + (size_t)p * 4096, &w_map, wfull, 0, wrow, 0);
+        // 64 channels: the lo halves of all blocks sit behind the hi halves (a chunk of blocks stays contiguous in both)
+        if (CIN == 64) tma_load_3d(wsm + (size_t)(a.NW + p) * 4096, &w_map, wfull, 64, wrow, 0);
+      }
       // everything above is independent of the previous kernel in the stream
       asm volatile("griddepcontrol.wait;" ::: "memory");
       rb_stamp(a, 2);
-      const uint32_t tile_bytes = a.mode == 0 ? (uint32_t)(a.G * a.d * 128) : (uint32_t)RB_TILE_BYTES;
+      const uint32_t tile_bytes = (a.mode == 0 ? (uint32_t)(a.G * a.d * 128) : 16384u) * (CIN / 32);
       int st = 0;
       uint32_t empty_phase = ~0u;
       Span s;
@@ -251,10 +262,12 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
               r0 += q * a.S;
               j0 -= q;
             }
-            tma_load_4d(ring + (size_t)st * RB_TILE_BYTES, &in_map, &full[st], 0, (int)r0, (int)j0, s.b);
+            tma_load_4d(ring + (size_t)st * TILE, &in_map, &full[st], 0, (int)r0, (int)j0, s.b);
+            if (CIN == 64) tma_load_4d(ring + (size_t)st * TILE + 16384, &in_map, &full[st], 64, (int)r0, (int)j0, s.b);
           } else {
             const long long row = a.in_row0 + (s.m * a.n + i) * a.d + 128LL * s.l;
-            tma_load_3d(ring + (size_t)st * RB_TILE_BYTES, &in_map, &full[st], 0, (int)row, s.b);
+            tma_load_3d(ring + (size_t)st * TILE, &in_map, &full[st], 0, (int)row, s.b);
+            if (CIN == 64) tma_load_3d(ring + (size_t)st * TILE + 16384, &in_map, &full[st], 64, (int)row, s.b);
           }
           if (sp == sp0) rb_step_stamp(a, 3, i + km1);
           st = (st + 1 == a.stages) ? 0 : st + 1;
@@ -274,13 +287,22 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
       // product term c: A chunk offset / B chunk offset in 16-byte units within the 128-byte row
       // (row = [hi ch 0-15 | hi ch 16-31 | lo ch 0-15 | lo ch 16-31])
       //   xh*wh (2 slices), xh*wl (2 slices), xl*wh (2 slices)
-      constexpr uint32_t a_off[6] = {0, 2, 0, 2, 4, 6};
-      constexpr uint32_t b_off[6] = {0, 2, 4, 6, 0, 2};
+      // 32 channels: one 128-byte row holds both halves.  64 channels: the lo half is the second sub-tile (A: + 16 KB,
+      // B: behind the NW hi sub-tiles), slices at 0, 32, 64, 96 bytes of the 128-byte row
+      const uint32_t wlo = (uint32_t)a.NW * 256u;
+      auto a_off = [](int c) -> uint32_t {
+        if (CIN == 32) { constexpr uint32_t t[6] = {0, 2, 0, 2, 4, 6}; return t[c]; }
+        return (c >= 2 * KS ? 1024u : 0u) + 2u * (uint32_t)(c % KS);
+      };
+      auto b_off = [&](int c) -> uint32_t {
+        if (CIN == 32) { constexpr uint32_t t[6] = {0, 2, 4, 6, 0, 2}; return t[c]; }
+        return ((c >= KS && c < 2 * KS) ? wlo : 0u) + 2u * (uint32_t)(c % KS);
+      };
       // D[:, 32*slot .. 32*(slot+nb)) (+)= X * [blocks b0 .. b0+nb)^T for product term c
       auto mma = [&](uint32_t a_lo, int slot, int b0, int nb, int c, uint32_t acc) {
         const uint32_t idesc = idesc0 | ((uint32_t)(nb * 4) << 17);     // N = 32 * nb
-        const uint64_t da = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (a_lo + a_off[c]);
-        const uint64_t db = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (w_lo32 + (uint32_t)b0 * 256u + b_off[c]);
+        const uint64_t da = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (a_lo + a_off(c));
+        const uint64_t db = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (w_lo32 + (uint32_t)b0 * 256u + b_off(c));
         if (!(a.dbg & 2)) umma_f16(tmem + (uint32_t)(slot * 32), da, db, idesc, acc);
       };
       // steady-state chunks of the slot ring: [0, h0) and [h0, NS)
@@ -312,7 +334,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           full_phase ^= 1u << st;
           tc_fence_after();
           if (e == 0 && i == -km1 && leader_real) rb_stamp(a, 4);
-          const uint32_t a_lo = ring_lo + (uint32_t)st * (RB_TILE_BYTES >> 4);
+          const uint32_t a_lo = ring_lo + (uint32_t)st * (TILE >> 4);
           const int len = i + a.k;                  // blocks -i .. k-1  ->  slots 0 .. len-1
           const int nf = len - 1;                   // slots already started
           const int nfr = (i == 0) ? 2 : 1;         // slots started now: y_{len-1} (+ residual of step 0)
@@ -321,7 +343,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           else if (nf > 0) mma(a_lo, 0, -i, nf, 0, 1u);
           mma(a_lo, nf, km1, nfr, 0, 0u);
 #pragma unroll
-          for (int c = 1; c < 6; ++c) {
+          for (int c = 1; c < NT; ++c) {
             if (tb > 8) { mma(a_lo, 0, -i, 8, c, 1u); mma(a_lo, 8, -i + 8, tb - 8, c, 1u); }
             else mma(a_lo, 0, -i, tb, c, 1u);
           }
@@ -342,7 +364,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           mbar_wait(&full[st], (full_phase >> st) & 1u);
           full_phase ^= 1u << st;
           tc_fence_after();
-          const uint32_t a_lo = ring_lo + (uint32_t)st * (RB_TILE_BYTES >> 4);
+          const uint32_t a_lo = ring_lo + (uint32_t)st * (TILE >> 4);
           const int f1 = islot >= 1 ? islot - 1 : islot - 1 + NS;     // (i-1) mod NS
           const int f2 = f1 >= 1 ? f1 - 1 : f1 - 1 + NS;              // (i-2) mod NS
           // block of slot 0 is (0 - i) mod NS; the weights are stored twice so that a chunk never wraps
@@ -380,7 +402,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                 int b0 = bz + lo;
                 if (b0 >= NS) b0 -= NS;
 #pragma unroll
-                for (int c = 0; c < 6; ++c) mma(a_lo, lo, b0, hi - lo, c, 1u);
+                for (int c = 0; c < NT; ++c) mma(a_lo, lo, b0, hi - lo, c, 1u);
               }
             };
             if (nchunk == 2 && f1 >= h0) {    // the chunk of the freshly drained slot goes last
@@ -397,25 +419,25 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             const int b1 = bz + h0 >= NS ? bz + h0 - NS : bz + h0;
             if (!fresh0) {
 #pragma unroll
-              for (int c = 0; c < 6; ++c) mma(a_lo, 0, bz, h0, c, 1u);
+              for (int c = 0; c < NT; ++c) mma(a_lo, 0, bz, h0, c, 1u);
               wait_drain();
 #pragma unroll
-              for (int c = 0; c < 6; ++c) mma(a_lo, h0, b1, NS - h0, c, 1u);
+              for (int c = 0; c < NT; ++c) mma(a_lo, h0, b1, NS - h0, c, 1u);
             } else if (!fresh1) {
 #pragma unroll
-              for (int c = 0; c < 6; ++c) mma(a_lo, h0, b1, NS - h0, c, 1u);
+              for (int c = 0; c < NT; ++c) mma(a_lo, h0, b1, NS - h0, c, 1u);
               wait_drain();
 #pragma unroll
-              for (int c = 0; c < 6; ++c) mma(a_lo, 0, bz, h0, c, 1u);
+              for (int c = 0; c < NT; ++c) mma(a_lo, 0, bz, h0, c, 1u);
             } else {
               wait_drain();
 #pragma unroll
-              for (int c = 0; c < 6; ++c) { mma(a_lo, 0, bz, h0, c, 1u); mma(a_lo, h0, b1, NS - h0, c, 1u); }
+              for (int c = 0; c < NT; ++c) { mma(a_lo, 0, bz, h0, c, 1u); mma(a_lo, h0, b1, NS - h0, c, 1u); }
             }
           } else {
             wait_drain();
 #pragma unroll
-            for (int c = 0; c < 6; ++c) mma(a_lo, 0, bz, NS, c, 1u);
+            for (int c = 0; c < NT; ++c) mma(a_lo, 0, bz, NS, c, 1u);
           }
           umma_commit_if(&empty[st], leader_real);          // the tile may be overwritten once these MMAs have read it
           umma_commit_if(&done[e % NDONE], leader_real);    // y_i and its residual are complete
@@ -471,7 +493,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     // byte offset of chunk my_c inside the 128-byte output row
     int cbyte;
     if (ARCH == 0) cbyte = my_c * 16;
-    else if (a.out_fmt == FMT_SPLIT16) cbyte = (my_c < 2 ? 0 : 64) + grp * 32 + (my_c & 1) * 16;
+    else if (a.out_fmt == FMT_SPLIT16) cbyte = (my_c < 2 ? 0 : 2 * CIN) + grp * 32 + (my_c & 1) * 16;
     else cbyte = grp * 64 + my_c * 16;
     const float oscale = a.out_fmt == FMT_SPLIT16 ? kActScale : 1.0f;
     const float inv_sr = a.inv_sr * oscale;
@@ -490,7 +512,7 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         aff[lane] = __ldg(sc + lane) * a.inv_sw * oscale;
         aff[32 + lane] = __ldg(sh + lane) * oscale;
       } else {   // lanes 0..15: tanh half of this group, 16..31: sigmoid half (one padded width = 32 further)
-        const int src = (lane < 16) ? grp * 16 + lane : 32 + grp * 16 + (lane - 16);
+        const int src = (lane < 16) ? grp * 16 + lane : CIN + grp * 16 + (lane - 16);
         aff[lane] = __ldg(sc + src) * a.inv_sw;
         aff[32 + lane] = __ldg(sh + src);
       }
@@ -772,16 +794,21 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
 // weight blocks held in shared memory: block p = block p mod NS, far enough that a steady-state chunk
 // (<= ceil(NS/2) slots, or all NS when NS <= 8) starting at any block never wraps
 static int rb_weight_blocks(int NS) { return NS + (NS > 8 ? (NS + 1) / 2 : NS) - 1; }
-static size_t rb_smem_bytes(int NS, int stages) {
-  return (size_t)stages * RB_TILE_BYTES + (size_t)rb_weight_blocks(NS) * 4096 + (size_t)(4 * RB_ESETS) * (4096 + 256) + 512 +
+static size_t rb_smem_bytes(int NS, int stages, int cin = 32) {
+  return (size_t)stages * (cin * 512) + (size_t)rb_weight_blocks(NS) * (cin * 128) + (size_t)(4 * RB_ESETS) * (4096 + 256) + 512 +
          1024;
 }
 
-int ring_groups(int arch) { return arch == 1 ? 2 : 1; }
+// channel groups = CTAs that share an input tile: GCN 16 gate channels each
+int ring_groups(int arch, int C) { return arch == 1 ? C / 16 : 1; }
 
 bool ring_eligible(int arch, int Cin, int C, int k, int d) {
-  if (Cin != 32 || C != 32 || k < 1 || k + 1 > RB_MAX_SLOTS || d < 1) return false;
-  (void)arch;
+  if (Cin != C || k < 1 || k + 1 > RB_MAX_SLOTS || d < 1) return false;
+  if (C == 64) {   // GCN only; the weights (8 KB per block) must leave room for two input stages
+    if (arch != 1 || rb_smem_bytes(k + 1, 2, 64) > 227 * 1024) return false;
+  } else if (C != 32) {
+    return false;
+  }
   // share of the 128 tile rows that carry real samples
   double eff;
   if (d < 128) eff = (double)((128 / d) * d) / 128.0;
@@ -804,10 +831,10 @@ float ring_weight_scale(const float* w, size_t n) {
   return ldexpf(1.0f, 10 - e);
 }
 
-void ring_pack_weights(int arch, int grp, int k, const float* conv_w /*[W][32][k]*/, const float* res_w /*[32][32]*/,
-                       std::vector<uint16_t>& out, float* inv_sw, float* inv_sr, float force_sw, float force_sr) {
-  const int W = arch == 1 ? 64 : 32, C = 32, NS = k + 1;
-  out.assign((size_t)NS * 32 * 64, 0);
+void ring_pack_weights(int arch, int grp, int k, const float* conv_w /*[W][C][k]*/, const float* res_w /*[C][C]*/,
+                       std::vector<uint16_t>& out, float* inv_sw, float* inv_sr, float force_sw, float force_sr, int C) {
+  const int W = arch == 1 ? 2 * C : C, NS = k + 1;
+  out.assign((size_t)NS * 32 * 2 * C, 0);
   const float sw = force_sw > 0.f ? force_sw : ring_weight_scale(conv_w, (size_t)W * C * k);
   const float sr = force_sr > 0.f ? force_sr : ring_weight_scale(res_w, (size_t)C * C);
   *inv_sw = 1.0f / sw;
@@ -815,16 +842,16 @@ void ring_pack_weights(int arch, int grp, int k, const float* conv_w /*[W][32][k
   auto put = [&](int block, int row, int ci, float v) {
     const __half h = __float2half_rn(v);
     const __half l = __float2half_rn(v - __half2float(h));
-    const size_t base = ((size_t)block * 32 + row) * 64;
+    const size_t base = ((size_t)block * 32 + row) * 2 * C;   // row = [hi C ch | lo C ch]
     out[base + ci] = __half_as_ushort(h);
-    out[base + 32 + ci] = __half_as_ushort(l);
+    out[base + C + ci] = __half_as_ushort(l);
   };
   for (int s = 0; s < k; ++s) {
     const int j = k - 1 - s;
     for (int n = 0; n < 32; ++n) {
       int ch;
       if (arch == 0) ch = n;
-      else ch = (n < 16) ? 16 * grp + n : 32 + 16 * grp + (n - 16);
+      else ch = (n < 16) ? 16 * grp + n : C + 16 * grp + (n - 16);
       for (int ci = 0; ci < C; ++ci) put(s, n, ci, conv_w[((size_t)ch * C + ci) * k + j] * sw);
     }
   }
@@ -836,11 +863,11 @@ void ring_pack_weights(int arch, int grp, int k, const float* conv_w /*[W][32][k
 }
 
 static bool make_group_map(CUtensorMap* map, const void* base, uint64_t rext, uint64_t jext, uint64_t clips,
-                           uint64_t S_rows, uint64_t clip_stride_elems, uint32_t d, uint32_t G) {
+                           uint64_t S_rows, uint64_t clip_stride_elems, uint32_t d, uint32_t G, uint64_t row_elems = 64) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
-  cuuint64_t dims[4] = {64, rext, jext, clips};
-  cuuint64_t strides[3] = {128, S_rows * 128, clip_stride_elems * 2};
+  cuuint64_t dims[4] = {row_elems, rext, jext, clips};
+  cuuint64_t strides[3] = {row_elems * 2, S_rows * row_elems * 2, clip_stride_elems * 2};
   cuuint32_t box[4] = {64, d, G, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
@@ -850,8 +877,8 @@ static bool make_group_map(CUtensorMap* map, const void* base, uint64_t rext, ui
 
 // Host-side launch plan (no CUDA calls; unit-tested on the CPU through nasr_debug_ring_plan): walk mode, span length,
 // grid, shared-memory stages, TMEM columns.  In: a.{B, T, k, d, in_row0}; cached_n > 0 skips the span-length search.
-cudaError_t ring_plan(int arch, int sm_count, long long cached_n, RingArgs& a, long long* grid_out) {
-  const int n_grp = ring_groups(arch);
+cudaError_t ring_plan(int arch, int sm_count, long long cached_n, RingArgs& a, long long* grid_out, int cin) {
+  const int n_grp = ring_groups(arch, cin);
   a.n_grp = n_grp;
   a.NS = a.k + 1;
   if (a.NS > RB_MAX_SLOTS) return cudaErrorInvalidConfiguration;
@@ -859,9 +886,9 @@ cudaError_t ring_plan(int arch, int sm_count, long long cached_n, RingArgs& a, l
   a.tmem_cols = 32;
   while (a.tmem_cols < a.NS * 32) a.tmem_cols *= 2;
   int stages = RB_MAX_STAGES;
-  while (stages > 2 && rb_smem_bytes(a.NS, stages) > 227 * 1024) --stages;
+  while (stages > 2 && rb_smem_bytes(a.NS, stages, cin) > 227 * 1024) --stages;
   a.stages = stages;
-  if (rb_smem_bytes(a.NS, stages) > 227 * 1024) return cudaErrorInvalidConfiguration;
+  if (rb_smem_bytes(a.NS, stages, cin) > 227 * 1024) return cudaErrorInvalidConfiguration;
 
   // ---- span length: n steps per span; every span pays k - 1 warm-up steps (loads + partial MMAs) ----
   long long steps_per_strip;   // steps a whole strip needs when it is one span
@@ -945,7 +972,7 @@ int ring_debug_steps(unsigned long long* host) {
 cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   RingArgs a = L.a;
   if (a.B <= 0 || a.T <= 0) return cudaSuccess;
-  if (a.out_row_bytes <= 0) a.out_row_bytes = 128;
+  if (a.out_row_bytes <= 0) a.out_row_bytes = L.cin * 4;
   if (!L.acc && (a.pin || a.raw_out)) return cudaErrorInvalidValue;
   {
     static int dbg = -1;
@@ -968,17 +995,19 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   }
   RingMapCache local;
   RingMapCache* c = L.cache ? L.cache : &local;
-  const int n_grp = ring_groups(L.arch);
+  const int cin = L.cin;
+  if (cin != 32 && !(cin == 64 && L.arch == 1 && !L.acc)) return cudaErrorInvalidConfiguration;
+  const int n_grp = ring_groups(L.arch, cin);
   long long grid = 0;
   {
     long long cached_n = 0;
     if (c->n_B == a.B && c->n_T == a.T && c->n_d == a.d && c->n_k == a.k && c->n_row0 == a.in_row0 && c->n_sm == L.sm_count)
       cached_n = c->n;
-    cudaError_t perr = ring_plan(L.arch, L.sm_count, cached_n, a, &grid);
+    cudaError_t perr = ring_plan(L.arch, L.sm_count, cached_n, a, &grid, cin);
     if (perr != cudaSuccess) return perr;
     c->n_B = a.B; c->n_T = a.T; c->n_d = a.d; c->n_k = a.k; c->n_row0 = a.in_row0; c->n_sm = L.sm_count; c->n = a.n;
   }
-  const size_t smem = rb_smem_bytes(a.NS, a.stages);
+  const size_t smem = rb_smem_bytes(a.NS, a.stages, cin);
 
   static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
   CUtensorMap& in_map = *reinterpret_cast<CUtensorMap*>(c->in_map);
@@ -992,9 +1021,9 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
       const uint64_t rext = (uint64_t)((a.in_row0 > 0 ? a.in_row0 : 0) + a.S + a.d);
       const uint64_t jext = (uint64_t)((L.in_rows + a.S - 1) / a.S);
       ok = make_group_map(&in_map, L.in, rext, jext, (uint64_t)a.B, (uint64_t)a.S, (uint64_t)L.in_clip_stride_elems,
-                          (uint32_t)a.d, (uint32_t)a.G);
+                          (uint32_t)a.d, (uint32_t)a.G, (uint64_t)cin * 2);
     } else {
-      ok = make_plane_map(&in_map, L.in, 64, (uint64_t)L.in_rows, (uint64_t)a.B, (uint64_t)L.in_clip_stride_elems, 128);
+      ok = make_plane_map(&in_map, L.in, (uint64_t)cin * 2, (uint64_t)L.in_rows, (uint64_t)a.B, (uint64_t)L.in_clip_stride_elems, 128);
     }
     if (!ok) return cudaErrorInvalidValue;
     c->in = L.in; c->in_rows = L.in_rows; c->in_stride = L.in_clip_stride_elems; c->B = a.B;
@@ -1028,15 +1057,18 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   }
   if (c->w != L.wpacked || c->NS != a.NS) {
     const uint64_t rows = (uint64_t)n_grp * a.NS * 32;
-    if (!make_plane_map(&w_map, L.wpacked, 64, rows, 1, rows * 64, 32)) return cudaErrorInvalidValue;
+    if (!make_plane_map(&w_map, L.wpacked, (uint64_t)cin * 2, rows, 1, rows * cin * 2, 32)) return cudaErrorInvalidValue;
     c->w = L.wpacked; c->NS = a.NS;
   }
 
   cudaError_t err;
-  static unsigned long long attr_set[4] = {0, 0, 0, 0};
-  const void* fn = L.arch == 0 ? (L.acc ? (const void*)ring_block_kernel<0, true> : (const void*)ring_block_kernel<0, false>)
-                               : (L.acc ? (const void*)ring_block_kernel<1, true> : (const void*)ring_block_kernel<1, false>);
-  if (attr_needed_on_this_device(attr_set[L.arch + (L.acc ? 2 : 0)])) {
+  static unsigned long long attr_set[5] = {0, 0, 0, 0, 0};
+  const void* fn;
+  int fi;
+  if (cin == 64) { fn = (const void*)ring_block_kernel<1, false, 64>; fi = 4; }
+  else if (L.arch == 0) { fn = L.acc ? (const void*)ring_block_kernel<0, true, 32> : (const void*)ring_block_kernel<0, false, 32>; fi = L.acc ? 2 : 0; }
+  else { fn = L.acc ? (const void*)ring_block_kernel<1, true, 32> : (const void*)ring_block_kernel<1, false, 32>; fi = L.acc ? 3 : 1; }
+  if (attr_needed_on_this_device(attr_set[fi])) {
     err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (err != cudaSuccess) return err;
   }
@@ -1050,10 +1082,11 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = L.pdl ? 1 : 0;
-  if (L.arch == 0 && !L.acc) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<0, false>, in_map, w_map, out_map, a);
-  else if (L.arch == 0) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<0, true>, in_map, w_map, out_map, a);
-  else if (!L.acc) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<1, false>, in_map, w_map, out_map, a);
-  else err = cudaLaunchKernelEx(&cfg, ring_block_kernel<1, true>, in_map, w_map, out_map, a);
+  if (cin == 64) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<1, false, 64>, in_map, w_map, out_map, a);
+  else if (L.arch == 0 && !L.acc) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<0, false, 32>, in_map, w_map, out_map, a);
+  else if (L.arch == 0) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<0, true, 32>, in_map, w_map, out_map, a);
+  else if (!L.acc) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<1, false, 32>, in_map, w_map, out_map, a);
+  else err = cudaLaunchKernelEx(&cfg, ring_block_kernel<1, true, 32>, in_map, w_map, out_map, a);
   if (err != cudaSuccess) return err;
   return cudaGetLastError();
 }

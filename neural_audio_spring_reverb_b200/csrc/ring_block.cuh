@@ -47,7 +47,7 @@ struct RingArgs {
   long long pin_clip_stride;   // floats between clips
   int pin_ld;              // floats per row (32 * n_grp)
   int raw_out;             // 1: write the raw conv sums (+ pin) to `out` (same layout as pin) instead of the block's output
-  int out_row_bytes;       // bytes per output plane row (0 = 128)
+  int out_row_bytes;       // bytes per output plane row (0 = 4 bytes per channel of the block)
   int l2_prefetch;         // > 0: TMA-prefetch the input tile of that many steps ahead into L2
   unsigned long long* prof;      // nasr_forward_profiled: {start, end} stamps of this launch, or NULL
   unsigned long long* dbg_buf;   // dev only: per-CTA timeline stamps
@@ -79,23 +79,24 @@ struct RingLaunch {
   int arch, sm_count;
   bool pdl = false;                 // programmatic dependent launch (prologue overlaps the previous kernel's tail)
   bool acc = false;                 // tap-pass variant of the kernel (a.pin / a.raw_out honoured)
+  int cin = 32;                     // channels of the block (32, or 64 for GCN): plane rows are cin * 4 bytes
   RingArgs a;
 };
 
 // eligibility: 32 -> 32 channels, k + 1 accumulator slots fit TMEM, and the tile rows are
 // well used for this dilation
 bool ring_eligible(int arch, int Cin, int C, int k, int d);
-// number of weight groups (launches per block): 1 for TCN, 2 for GCN
-int ring_groups(int arch);
+// channel groups (CTAs that share an input tile, each with its own weights): 1 for TCN, C / 16 for GCN
+int ring_groups(int arch, int C = 32);
 // force_sw / force_sr > 0: use these power-of-two weight scales instead of deriving them from the arrays (tap passes
 // of one block must share them)
 void ring_pack_weights(int arch, int grp, int k, const float* conv_w, const float* res_w, std::vector<uint16_t>& out,
-                       float* inv_sw, float* inv_sr, float force_sw = 0.f, float force_sr = 0.f);
+                       float* inv_sw, float* inv_sr, float force_sw = 0.f, float force_sr = 0.f, int C = 32);
 float ring_weight_scale(const float* w, size_t n);
 cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s);
 int ring_debug_stamps(unsigned long long* host, int max_ctas);
 int ring_debug_steps(unsigned long long* host);
-cudaError_t ring_plan(int arch, int sm_count, long long cached_n, RingArgs& a, long long* grid_out);
+cudaError_t ring_plan(int arch, int sm_count, long long cached_n, RingArgs& a, long long* grid_out, int cin = 32);
 int ring_debug_plan(int arch, int k, int d, int B, long long T, long long in_row0, int sm_count, long long* out16);
 
 }  // namespace nasr

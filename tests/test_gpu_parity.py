@@ -455,6 +455,38 @@ def test_tap_pass_shapes(arch, n_blocks, C, k, g):
     assert m.saturated() is False
 
 
+WIDE_SHAPES = [
+    # GCN with 64 channels (the shipped GCN-3 / GCN-springset shape): 256-byte plane rows, four channel groups per tile
+    (3, 3, 256), (4, 3, 32), (3, 5, 7), (3, 2, 200), (3, 9, 2), (2, 1, 3),
+]
+
+
+@pytest.mark.parametrize("n_blocks,k,g", WIDE_SHAPES)
+def test_gcn_64_channels_on_the_ring_kernel(n_blocks, k, g):
+    import neural_audio_spring_reverb_b200 as N
+    cfg = dict(arch="GCN", n_blocks=n_blocks, n_channels=64, kernel_size=k, dilation_growth=g, cond_dim=2)
+    sd = O.build_state("GCN", n_blocks, 64, k, 2, seed=64 + k + g)
+    dil = [g ** i for i in range(n_blocks)]
+    m = build_model(cfg, sd, DEV)
+    assert [m._engine().block_path(i) for i in range(n_blocks)] == [0] + [2] * (n_blocks - 1)
+    rf = O.receptive_field(k, dil) if k > 1 else 1
+    T = min(max(2 * rf, 9000), 150000) + 37
+    x = O.make_input(2, 1, T)
+    cond = torch.tensor([[0.2, 0.9], [0.7, 0.1]])
+    ref = O.forward(sd, dil, x, cond)
+    y = m(x.to(DEV), cond.to(DEV))
+    assert rel_err(y, ref) <= REL_TOL
+    st = N.CachedStream(m)
+    outs, s0 = [], 0
+    for n in (1, 130, 4099, 777, 10**9):
+        if s0 >= T:
+            break
+        outs.append(st(x[..., s0:s0 + n].to(DEV), cond.to(DEV)))
+        s0 += n
+    assert rel_err(torch.cat(outs, -1), ref) <= REL_TOL
+    assert m.saturated() is False
+
+
 def test_sixteen_channel_nets_run_on_the_tensor_core_kernels():
     """16 <= C < 32 (BASELINE config 1, the shipped WaveNets): planes padded to 32 channels, blocks 1.. on the ring kernel."""
     cfg = O.CONFIGS["cfg1"]
