@@ -526,6 +526,57 @@ def run_cfg5(ctx, args):
     return rec
 
 
+def run_shipped(ctx, args):
+    """The reference's own shipped checkpoints (weights in tests/golden): one 10 s clip at the checkpoint's sample rate,
+    device-resident, on the kernels the engine picks by default next to the fp32 FFMA kernels (NASR_PATH=fp32), with
+    the parity of the default path against the golden vector the reference produced."""
+    import sys
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "tests"))
+    from util import build_model as build_from_state, golden_inputs, golden_names, load_golden, rel_err
+    rec = dict(workload="shipped checkpoints: 1 clip x 10 s each, device-resident, L2 flushed; Msamples/s default path vs "
+                        "NASR_PATH=fp32 (FFMA kernels); block_path 0 = FFMA, 1 = tcgen05 tap gather, 2 = tcgen05 ring, "
+                        "3 = ring in tap passes", replicas=ctx.world, checkpoints={})
+    old = os.environ.get("NASR_PATH")
+    for name in golden_names():
+        if not name.startswith("ckpt_") or name.endswith("_cond"):
+            continue
+        meta, y_ref, sd = load_golden(name)
+        cfg = meta["cfg"]
+        T = 10 * cfg.get("sample_rate", SR)
+        g = torch.Generator(device=ctx.dev).manual_seed(7)
+        x = torch.rand((1, 1, T), device=ctx.dev, generator=g) * 2 - 1
+        cond = torch.tensor([[0.3, 0.7]], device=ctx.dev) if cfg["cond_dim"] else None
+        gx, gc = golden_inputs(meta)
+        r = dict(arch=cfg["arch"], channels=cfg["n_channels"], kernel_size=cfg["kernel_size"], dilations=meta.get("dilations"))
+        for mode in ("auto", "fp32"):
+            os.environ["NASR_PATH"] = mode
+            m = build_from_state(cfg, sd, ctx.dev)
+            m.set_async(True)
+            if mode == "auto":
+                r["parity_vs_reference_golden"] = rel_err(m(gx.to(ctx.dev), None if gc is None else gc.to(ctx.dev)), y_ref)
+                r["block_paths"] = [m._engine().block_path(i) for i in range(len(meta.get("dilations") or [0] * cfg["n_blocks"]))]
+            for _ in range(3):
+                m(x, cond)
+            ms = []
+            for _ in range(5):
+                ctx.flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                m(x, cond)
+                e1.record()
+                torch.cuda.synchronize(ctx.dev)
+                ms.append(e0.elapsed_time(e1))
+            r["msamples_per_s" if mode == "auto" else "msamples_per_s_fp32"] = round(T / sorted(ms)[2] / 1e3, 1)
+            m.release_engine()
+        rec["checkpoints"][name[5:]] = r
+    if old is None:
+        os.environ.pop("NASR_PATH", None)
+    else:
+        os.environ["NASR_PATH"] = old
+    torch.cuda.empty_cache()
+    return rec
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -535,7 +586,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--clips-per-gpu", type=int, default=1)
-    ap.add_argument("--configs", default="cfg3,cfg4,cfg5", help="sub-records to add to the line ('' = none)")
+    ap.add_argument("--configs", default="cfg3,cfg4,cfg5,shipped", help="sub-records to add to the line ('' = none)")
     ap.add_argument("--cfg4-clips", type=int, default=64, help="clips per GPU of the cfg4 sub-record")
     ap.add_argument("--cfg5-seconds", type=float, default=3600.0, help="stream length of the cfg5 sub-record")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="clip length of the CPU baseline sample")
@@ -657,7 +708,7 @@ def main():
     model.release_engine()
     subs = {}
     want = [c for c in args.configs.split(",") if c]
-    runners = dict(cfg3=run_cfg3, cfg4=run_cfg4, cfg5=run_cfg5)
+    runners = dict(cfg3=run_cfg3, cfg4=run_cfg4, cfg5=run_cfg5, shipped=run_shipped)
     for name in want:
         if name not in runners:
             raise SystemExit(f"unknown sub-record {name!r}")

@@ -77,3 +77,38 @@ def test_toeplitz_tile_times_stacked_weights_is_block0(Cin, k, d):
                 want_conv[t] += conv_w[:, :, j] @ x[:, tt]
     assert np.allclose(D[:, :W], want_conv, atol=1e-10)
     assert np.allclose(D[:, W:], (res_w @ x).T, atol=1e-10)
+
+
+# ---- tap passes (engine.cu path 3): a k-tap block as several <= 15-tap convolutions on shifted input ----
+@pytest.mark.parametrize("k,d,taps", [(99, 14, 15), (99, 512, 15), (46, 3, 15), (45, 1, 15), (20, 5, 15), (7, 2, 3), (2, 1, 1)])
+def test_tap_passes_add_up_to_the_full_convolution(k, d, taps):
+    """Pass p takes the kernel positions j in [k - tap0 - kp, k - tap0) (tap0 = p * taps, kp <= taps) and reads the
+    input tap0 * d rows earlier (rows before the clip are the causal zero fill); the passes run oldest taps first and
+    hand fp32 sums on, the last one (tap0 = 0) reads the input unshifted and is the one that can carry the residual."""
+    rng = np.random.default_rng(k * 1000 + d)
+    C, W, T = 4, 6, 3 * (k - 1) * d // 2 + 50
+    x = rng.standard_normal((C, T))
+    w = rng.standard_normal((W, C, k))
+
+    def causal_conv(xx, ww, dd):
+        kk = ww.shape[-1]
+        xp = np.concatenate([np.zeros((xx.shape[0], (kk - 1) * dd)), xx], axis=1)
+        out = np.zeros((ww.shape[0], xx.shape[1]))
+        for j in range(kk):
+            out += ww[:, :, j] @ xp[:, j * dd: j * dd + xx.shape[1]]
+        return out
+
+    ref = causal_conv(x, w, d)
+    n_pass = (k + taps - 1) // taps
+    partial = np.zeros_like(ref)
+    order = []
+    for q in range(n_pass):
+        tap0 = (n_pass - 1 - q) * taps
+        kp = min(taps, k - tap0)
+        j0 = k - tap0 - kp
+        shift = tap0 * d
+        xs = np.concatenate([np.zeros((C, shift)), x], axis=1)[:, :T]      # in_row0 - tap0 * d: earlier rows, zero fill
+        partial += causal_conv(xs, w[:, :, j0:j0 + kp], d)
+        order.append(tap0)
+    assert order[-1] == 0 and sorted(order, reverse=True) == order
+    np.testing.assert_allclose(partial, ref, rtol=1e-10, atol=1e-10)

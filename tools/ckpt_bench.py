@@ -74,6 +74,17 @@ def main():
             row[f"{mode}_ms"] = ms
             row[f"{mode}_msps"] = T / ms / 1e3
             ys[mode] = m(x, cond)
+            if mode == "auto":   # per-block device time in the pipelined forward (kernel-side stamps)
+                yb = torch.empty((1, 1, T), device=DEV)
+                st = torch.cuda.current_stream().cuda_stream
+                if cond is not None:
+                    eng.set_cond(cond.data_ptr(), 1, st)
+                acc = None
+                for _ in range(3):
+                    flush.fill_(1.0)
+                    msb = eng.forward_profiled(x.data_ptr(), yb.data_ptr(), 1, T, st)
+                    acc = msb if acc is None else [p + q for p, q in zip(acc, msb)]
+                row["auto_block_us"] = [round(v / 3 * 1e3, 1) for v in acc]
             row[f"{mode}_saturated"] = bool(m.saturated())
         os.environ["NASR_PATH"] = "auto"
         row["auto_vs_fp32_full"] = rel_err(ys["auto"], ys["fp32"])
@@ -82,7 +93,7 @@ def main():
         print(f"{row['name']:46s} {row['arch']:7s} C={row['C']:<3d} k={row['k']:<3d} paths={row['auto_paths']} "
               f"auto {row['auto_ms']:.3f} ms ({row['auto_msps']:.0f} Msamples/s, parity {row['auto_parity']:.1e}) "
               f"fp32 {row['fp32_ms']:.3f} ms ({row['fp32_msps']:.0f} Ms/s, parity {row['fp32_parity']:.1e}) "
-              f"x{row['speedup']:.2f}  full-clip auto vs fp32 {row['auto_vs_fp32_full']:.1e}", flush=True)
+              f"x{row['speedup']:.2f}  full-clip auto vs fp32 {row['auto_vs_fp32_full']:.1e}  block us {row['auto_block_us']}", flush=True)
     if args.json:
         Path(args.json).write_text(json.dumps(rows, indent=1))
 
