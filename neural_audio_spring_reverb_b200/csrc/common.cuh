@@ -108,7 +108,7 @@ struct CopyJob {
   int segs;
   int vec;                            // filled in by launch_copy_multi
 };
-cudaError_t launch_copy_multi(const CopyJob* jobs, int n, cudaStream_t s);
+cudaError_t launch_copy_multi(const CopyJob* jobs, int n, cudaStream_t s, bool pdl = false);
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);

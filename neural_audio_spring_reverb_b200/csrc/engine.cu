@@ -104,6 +104,7 @@ struct nasr_engine {
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   DevBuf hx2[2], hy2[2];
   bool small_gather = true;   // NASR_SMALL_GATHER=0: ring kernel for every launch size (dev)
+  int gather_tiles_per_sm = 4;   // NASR_GATHER_TILES: launches with fewer tiles per SM run the tap-gather kernel (measured with PDL on both kernels: 65 536-sample chunks of cfg2, 3.5 tiles per SM, 152 us vs 161 us on the ring kernel)
   bool stream_graph = true;   // NASR_STREAM_GRAPH=0: streaming chunks as plain launches (dev)
   // streaming: CUDA graphs of one chunk's launches, keyed by (B, T_chunk); x is staged into plane 0 and y leaves through
   // ychunk by plain device copies around the graph launch, so the graph's kernel arguments never change
@@ -281,12 +282,12 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
   // costs more than the tap-gather kernel's smaller instructions (measured on cfg2 streams: 1 024-sample chunks 110 vs
   // 129 us per chunk with the tap-gather kernel, 65 536-sample chunks 172 vs 166 us)
   const long long tiles = (long long)a.B * ((a.T + 127) / 128);
-  const bool small_launch = bs.path == 2 && bs.wtg && e->small_gather && tiles < 2LL * e->sm_count;
+  const bool small_launch = bs.path == 2 && bs.wtg && e->small_gather && tiles < (long long)e->gather_tiles_per_sm * e->sm_count;
   if (allow_tc && tc_chain && (bs.path == 1 || small_launch)) {
     TcLaunch L{};
     L.cache = &e->tc_cache[i];
     L.in = a.in; L.in_rows = a.in_rows; L.in_clip_stride_elems = a.in_clip_stride;
-    L.wpacked = small_launch ? bs.wtg : bs.wtc; L.arch = e->desc.arch; L.sm_count = e->sm_count;
+    L.wpacked = small_launch ? bs.wtg : bs.wtc; L.arch = e->desc.arch; L.sm_count = e->sm_count; L.pdl = e->pdl;
     TcArgs& t = L.a;
     t.out = a.out; t.out_fmt = a.out_fmt; t.out_clip_stride = a.out_clip_stride; t.out_rows = a.out_rows;
     t.out_row0 = a.out_row0; t.in_row0 = a.in_row0; t.B = a.B; t.T = a.T; t.k = a.k; t.d = a.d;
@@ -480,6 +481,7 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
   if (const char* env = getenv("NASR_ZEROCOPY")) e->zero_copy = atoi(env) != 0;
   if (const char* env = getenv("NASR_HOST_PIPE")) e->host_pipe = atoi(env) != 0;
   if (const char* env = getenv("NASR_SMALL_GATHER")) e->small_gather = atoi(env) != 0;
+  if (const char* env = getenv("NASR_GATHER_TILES")) { const int v = atoi(env); if (v >= 1) e->gather_tiles_per_sm = v; }
   if (const char* env = getenv("NASR_STREAM_GRAPH")) e->stream_graph = atoi(env) != 0;
   const float* p = w;
   std::vector<FoldArgs> fold(n);
@@ -1199,7 +1201,7 @@ static int chunk_body(nasr_engine* e, float* y_out, int B, int64_t Tc, cudaStrea
   for (auto* jobs : {&first, &second}) {
     for (size_t q = 0; q < jobs->size(); q += NASR_MULTI_COPY_MAX) {
       const int cnt = (int)(jobs->size() - q < NASR_MULTI_COPY_MAX ? jobs->size() - q : NASR_MULTI_COPY_MAX);
-      NASR_CUDA(e, launch_copy_multi(jobs->data() + q, cnt, s));
+      NASR_CUDA(e, launch_copy_multi(jobs->data() + q, cnt, s, e->pdl));
       e->launches += 1;
     }
   }

@@ -161,6 +161,10 @@ struct MultiCopy {
 };
 
 __global__ void copy_multi_kernel(const __grid_constant__ MultiCopy mc) {
+  // programmatic dependent launch: resident early, but nothing moves before the kernels in front (which still read the
+  // rows this one overwrites) are complete
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   int j = 0;
   while (j + 1 < mc.n && (int)blockIdx.y >= mc.seg_begin[j + 1]) ++j;
   const CopyJob& c = mc.job[j];
@@ -178,7 +182,7 @@ __global__ void copy_multi_kernel(const __grid_constant__ MultiCopy mc) {
   }
 }
 
-cudaError_t launch_copy_multi(const CopyJob* jobs, int n, cudaStream_t s) {
+cudaError_t launch_copy_multi(const CopyJob* jobs, int n, cudaStream_t s, bool pdl) {
   if (n <= 0) return cudaSuccess;
   if (n > NASR_MULTI_COPY_MAX) return cudaErrorInvalidValue;
   MultiCopy mc{};
@@ -199,7 +203,17 @@ cudaError_t launch_copy_multi(const CopyJob* jobs, int n, cudaStream_t s) {
   long long gx = (max_bytes / 16 + 255) / 256;
   if (gx > 256) gx = 256;
   if (gx < 1) gx = 1;
-  copy_multi_kernel<<<dim3((unsigned)gx, (unsigned)segs), 256, 0, s>>>(mc);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)gx, (unsigned)segs);
+  cfg.blockDim = dim3(256);
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, copy_multi_kernel, mc);
+  if (err != cudaSuccess) return err;
   return cudaGetLastError();
 }
 

@@ -284,25 +284,26 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
       constexpr uint32_t idesc0 = make_idesc(FMT_F16, FMT_F16, 128, 0);
       const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t w_lo32 = ((smem_u32(wsm) & 0x3FFFFu) >> 4) | (1u << 16);
-      // product term c: A chunk offset / B chunk offset in 16-byte units within the 128-byte row
-      // (row = [hi ch 0-15 | hi ch 16-31 | lo ch 0-15 | lo ch 16-31])
-      //   xh*wh (2 slices), xh*wl (2 slices), xl*wh (2 slices)
-      // 32 channels: one 128-byte row holds both halves.  64 channels: the lo half is the second sub-tile (A: + 16 KB,
-      // B: behind the NW hi sub-tiles), slices at 0, 32, 64, 96 bytes of the 128-byte row
+      // product term c: A chunk offset / B chunk offset in 16-byte units: xh*wh, xh*wl, xl*wh, each over the 16-channel slices.
+      // 32 channels: one 128-byte row holds both halves (row = [hi ch 0-15 | hi ch 16-31 | lo ch 0-15 | lo ch 16-31]).
+      // 64 channels: the lo half is the second sub-tile (A: + 16 KB, B: behind the NW hi sub-tiles), slices at 0, 32,
+      // 64, 96 bytes of the 128-byte row
+      constexpr uint32_t a_off32[6] = {0, 2, 0, 2, 4, 6};
+      constexpr uint32_t b_off32[6] = {0, 2, 4, 6, 0, 2};
       const uint32_t wlo = (uint32_t)a.NW * 256u;
-      auto a_off = [](int c) -> uint32_t {
-        if (CIN == 32) { constexpr uint32_t t[6] = {0, 2, 0, 2, 4, 6}; return t[c]; }
-        return (c >= 2 * KS ? 1024u : 0u) + 2u * (uint32_t)(c % KS);
-      };
-      auto b_off = [&](int c) -> uint32_t {
-        if (CIN == 32) { constexpr uint32_t t[6] = {0, 2, 4, 6, 0, 2}; return t[c]; }
-        return ((c >= KS && c < 2 * KS) ? wlo : 0u) + 2u * (uint32_t)(c % KS);
-      };
       // D[:, 32*slot .. 32*(slot+nb)) (+)= X * [blocks b0 .. b0+nb)^T for product term c
       auto mma = [&](uint32_t a_lo, int slot, int b0, int nb, int c, uint32_t acc) {
         const uint32_t idesc = idesc0 | ((uint32_t)(nb * 4) << 17);     // N = 32 * nb
-        const uint64_t da = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (a_lo + a_off(c));
-        const uint64_t db = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (w_lo32 + (uint32_t)b0 * 256u + b_off(c));
+        uint32_t ao, bo;
+        if constexpr (CIN == 32) {
+          ao = a_off32[c];
+          bo = b_off32[c];
+        } else {
+          ao = (c >= 2 * KS ? 1024u : 0u) + 2u * (uint32_t)(c % KS);
+          bo = ((c >= KS && c < 2 * KS) ? wlo : 0u) + 2u * (uint32_t)(c % KS);
+        }
+        const uint64_t da = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (a_lo + ao);
+        const uint64_t db = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (w_lo32 + (uint32_t)b0 * 256u + bo);
         if (!(a.dbg & 2)) umma_f16(tmem + (uint32_t)(slot * 32), da, db, idesc, acc);
       };
       // steady-state chunks of the slot ring: [0, h0) and [h0, NS)

@@ -184,6 +184,9 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // programmatic dependent launch (streaming chunks are chains of small launches): the next kernel of the stream may
+  // start its own set-up now; everything of ours that depends on the previous kernel sits behind griddepcontrol.wait
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == TC_PRODUCER_WARP) {
     // ================================ TMA producer ================================
@@ -191,6 +194,7 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
       prefetch_tensormap(&in_map);
       mbar_arrive_expect_tx(wfull, (uint32_t)(a.pairs * PAIR_BYTES));
       for (int p = 0; p < a.pairs; ++p) tma_load_3d(wsm + (size_t)p * PAIR_BYTES, &w_map, wfull, 0, p * CW, 0);
+      asm volatile("griddepcontrol.wait;" ::: "memory");   // the input plane is the previous kernel's output
       Sched s(a);
       int pos = 0;
       uint32_t empty_phase = ~0u;   // bit p: parity to wait for on empty[p] (first pass falls through)
@@ -338,6 +342,7 @@ tc_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constan
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
     Sched s(a);
     long long q = 0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // scale / shift come from the fold kernel (ring_block.cu)
     while (s.next(a)) {
       for (int i = 0; i < s.Gc; ++i, ++q) {
         if ((int)(q % ESETS) != eset) continue;
@@ -561,15 +566,26 @@ cudaError_t launch_tc_block(const TcLaunch& L, cudaStream_t s) {
       err = cudaFuncSetAttribute(tc_block_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (err != cudaSuccess) return err;
     }
-    tc_block_kernel<0><<<(unsigned)grid, tc_threads<0>(), smem, s>>>(in_map, w_map, a);
   } else {
     static unsigned long long set1 = 0;
     if (attr_needed_on_this_device(set1)) {
       err = cudaFuncSetAttribute(tc_block_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (err != cudaSuccess) return err;
     }
-    tc_block_kernel<1><<<(unsigned)grid, tc_threads<1>(), smem, s>>>(in_map, w_map, a);
   }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)(L.arch == 0 ? tc_threads<0>() : tc_threads<1>()));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = L.pdl ? 1 : 0;
+  if (L.arch == 0) err = cudaLaunchKernelEx(&cfg, tc_block_kernel<0>, in_map, w_map, a);
+  else err = cudaLaunchKernelEx(&cfg, tc_block_kernel<1>, in_map, w_map, a);
+  if (err != cudaSuccess) return err;
   return cudaGetLastError();
 }
 

@@ -55,6 +55,7 @@ struct TcLaunch {
   long long in_clip_stride_elems;   // 16-bit elements between clips
   const void* wpacked;              // device buffer from tc_pack_weights
   int arch, sm_count;
+  bool pdl = false;                 // programmatic dependent launch (set-up overlaps the previous kernel's tail)
   TcArgs a;
 };
 
