@@ -104,7 +104,9 @@ struct nasr_engine {
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   DevBuf hx2[2], hy2[2];
   bool small_gather = true;   // NASR_SMALL_GATHER=0: ring kernel for every launch size (dev)
-  int gather_tiles_per_sm = 4;   // NASR_GATHER_TILES: launches with fewer tiles per SM run the tap-gather kernel (measured with PDL on both kernels: 65 536-sample chunks of cfg2, 3.5 tiles per SM, 152 us vs 161 us on the ring kernel)
+  int gather_tiles_per_sm = 2;   // NASR_GATHER_TILES: launches with fewer tiles per SM run the tap-gather kernel.  (4 was measured 5 % faster on
+                                 // 65 536-sample chunks of cfg2 - 152 vs 161 us - but then a chunked stream and the one-shot forward of
+                                 // the same clip run on different kernels and agree to 2e-6 instead of 1e-6; not worth it)
   bool stream_graph = true;   // NASR_STREAM_GRAPH=0: streaming chunks as plain launches (dev)
   // streaming: CUDA graphs of one chunk's launches, keyed by (B, T_chunk); x is staged into plane 0 and y leaves through
   // ychunk by plain device copies around the graph launch, so the graph's kernel arguments never change

@@ -9,15 +9,15 @@
 
 namespace nasr {
 
-constexpr int FB_ROWS = 256;      // samples per CTA tile
-constexpr int FB_THREADS = 128;   // each thread owns rows r and r + 128 of the tile
+constexpr int FB_THREADS = 128;   // each thread owns NR rows of the CTA's tile: r, r + 128, ... (NR = 2; 1 for 128 conv channels)
 
 // packed fp32x2 FMA (sm_100): halves the FMA instruction count of this issue-bound kernel
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
-template <int ARCH, int C>
+template <int ARCH, int C, int NR>
 __global__ void __launch_bounds__(FB_THREADS, ((ARCH == 1 ? 2 * C : C) > 32 ? 2 : 3)) first_block_kernel(const BlockArgs a, const float* __restrict__ w0) {
   constexpr int W = ARCH == 1 ? 2 * C : C;
+  constexpr int FB_ROWS = FB_THREADS * NR;   // samples per CTA tile
   extern __shared__ __align__(16) float fsm[];
   if (threadIdx.x == 0) prof_stamp(a.prof, 0);
   const int Cin = a.Cin, k = a.k, d = a.d;
@@ -62,27 +62,34 @@ __global__ void __launch_bounds__(FB_THREADS, ((ARCH == 1 ? 2 * C : C) > 32 ? 2 
     __syncthreads();
 
     const int r = threadIdx.x;
-    float2 acc0[W / 2], acc1[W / 2];   // rows r and r + 128
+    float2 accs[NR][W / 2];   // rows r, r + 128, ...
 #pragma unroll
-    for (int n = 0; n < W / 2; ++n) acc0[n] = acc1[n] = make_float2(0.f, 0.f);
+    for (int h = 0; h < NR; ++h)
+#pragma unroll
+      for (int n = 0; n < W / 2; ++n) accs[h][n] = make_float2(0.f, 0.f);
     for (int j = 0; j < k; ++j)
       for (int ci = 0; ci < Cin; ++ci) {
-        const float x0 = xs[ci * XW + r + j * d], x1 = xs[ci * XW + r + 128 + j * d];
-        const float2 xa = make_float2(x0, x0), xb = make_float2(x1, x1);
+        float2 xv[NR];
+#pragma unroll
+        for (int h = 0; h < NR; ++h) {
+          const float x0 = xs[ci * XW + r + 128 * h + j * d];
+          xv[h] = make_float2(x0, x0);
+        }
         const float4* wv = reinterpret_cast<const float4*>(ws + (j * Cin + ci) * W);
 #pragma unroll
         for (int n = 0; n < W / 4; ++n) {
           const float4 q = wv[n];
           const float2 qa = make_float2(q.x, q.y), qb = make_float2(q.z, q.w);
-          acc0[2 * n] = fma2(xa, qa, acc0[2 * n]);
-          acc0[2 * n + 1] = fma2(xa, qb, acc0[2 * n + 1]);
-          acc1[2 * n] = fma2(xb, qa, acc1[2 * n]);
-          acc1[2 * n + 1] = fma2(xb, qb, acc1[2 * n + 1]);
+#pragma unroll
+          for (int h = 0; h < NR; ++h) {
+            accs[h][2 * n] = fma2(xv[h], qa, accs[h][2 * n]);
+            accs[h][2 * n + 1] = fma2(xv[h], qb, accs[h][2 * n + 1]);
+          }
         }
       }
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const float2* acc = half ? acc1 : acc0;
+    for (int half = 0; half < NR; ++half) {
+      const float2* acc = accs[half];
       const int rr = r + 128 * half;
       const long long t = t0 + rr;
       float o[C];
@@ -166,15 +173,16 @@ __global__ void __launch_bounds__(FB_THREADS, ((ARCH == 1 ? 2 * C : C) > 32 ? 2 
   }
 }
 
-template <int ARCH, int C>
+template <int ARCH, int C, int NR = 2>
 static cudaError_t launch_fb(const BlockArgs& a, const float* w0, int sm_count, cudaStream_t s) {
   constexpr int W = ARCH == 1 ? 2 * C : C;
+  constexpr int FB_ROWS = FB_THREADS * NR;
   const int H = (a.k - 1) * a.d;
   const size_t smem = sizeof(float) * ((size_t)(FB_THREADS / 32) * 32 * C + (size_t)a.k * a.Cin * W + (size_t)a.Cin * C +
                                        (a.out_fmt == FMT_FINAL ? (size_t)a.out_ch * C : 0) + 2 * (size_t)W +
                                        (size_t)a.Cin * (H + FB_ROWS));
   if (smem > 100 * 1024) return cudaErrorNotSupported;
-  auto kern = first_block_kernel<ARCH, C>;
+  auto kern = first_block_kernel<ARCH, C, NR>;
   static size_t configured_dev[64] = {0};   // per device: the attribute is per (function, device)
   int dev = 0;
   cudaGetDevice(&dev);
@@ -205,6 +213,7 @@ cudaError_t launch_first_block(const BlockArgs& a, const float* w0, int sm_count
   } else {
     if (a.Cout == 16) return launch_fb<1, 16>(a, w0, sm_count, s);
     if (a.Cout == 32) return launch_fb<1, 32>(a, w0, sm_count, s);
+    if (a.Cout == 64) return launch_fb<1, 64, 1>(a, w0, sm_count, s);   // 128 conv channels: one row per thread
   }
   return cudaErrorNotSupported;
 }

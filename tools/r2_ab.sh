@@ -1,8 +1,7 @@
 # dev: streaming A/B inside one session
 mkdir -p gpurun_out
-for v in "NASR_GATHER_TILES=2" "NASR_GATHER_TILES=4" "NASR_GATHER_TILES=8" "NASR_GATHER_TILES=2 NASR_PDL=0"; do
+timeout 600 python -m pytest tests -m gpu -q -x -k "streaming or cfg5 or tensor_core_path" 2>&1 | tail -6
+for v in "NASR_CHAIN=1" "NASR_CHAIN=0" "NASR_CHAIN=1 NASR_GATHER_TILES=8" "NASR_CHAIN=0 NASR_GATHER_TILES=8"; do
   echo "== $v"
-  env $v python tools/stream_bench.py 2>&1 | grep streaming
+  env $v timeout 300 python tools/stream_bench.py 2>&1 | grep streaming
 done
-python tools/ring_exp.py 1 2>&1 | tail -2
-python -m pytest tests -m gpu -q -x -k "streaming or cfg5" 2>&1 | tail -2
