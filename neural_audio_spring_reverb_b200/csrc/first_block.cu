@@ -14,6 +14,16 @@ constexpr int FB_THREADS = 128;   // each thread owns NR rows of the CTA's tile:
 // packed fp32x2 FMA (sm_100): halves the FMA instruction count of this issue-bound kernel
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
+// gate non-linearities on the MUFU ex2 / rcp path, as in the tensor-core kernels (absolute error ~1e-7 on O(1) outputs)
+__device__ __forceinline__ float fb_tanh(float x) {
+  const float e = __expf(2.0f * x);            // inf for large x -> 1 - 0; 0 for very negative x -> 1 - 2
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+__device__ __forceinline__ float fb_sigmoid(float x) {
+  const float e = __expf(-x);
+  return e > 1e30f ? 0.0f : __fdividef(1.0f, 1.0f + e);
+}
+
 template <int ARCH, int C, int NR>
 __global__ void __launch_bounds__(FB_THREADS, ((ARCH == 1 ? 2 * C : C) > 32 ? 2 : 3)) first_block_kernel(const BlockArgs a, const float* __restrict__ w0) {
   constexpr int W = ARCH == 1 ? 2 * C : C;
@@ -107,8 +117,8 @@ __global__ void __launch_bounds__(FB_THREADS, ((ARCH == 1 ? 2 * C : C) > 32 ? 2 
         for (int c = 0; c < C / 2; ++c) {
           const float2 yt = fma2(acc[c], sc2[c], sh2[c]);
           const float2 ys = fma2(acc[C / 2 + c], sc2[C / 2 + c], sh2[C / 2 + c]);
-          o[2 * c] = tanhf(yt.x) * (1.0f / (1.0f + expf(-ys.x)));
-          o[2 * c + 1] = tanhf(yt.y) * (1.0f / (1.0f + expf(-ys.y)));
+          o[2 * c] = fb_tanh(yt.x) * fb_sigmoid(ys.x);
+          o[2 * c + 1] = fb_tanh(yt.y) * fb_sigmoid(ys.y);
         }
       }
       for (int ci = 0; ci < Cin; ++ci) {
