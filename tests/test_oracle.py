@@ -95,3 +95,26 @@ def test_postprocess_oracle_pinned_to_torchaudio():
         assert got.shape == ref.shape == (1, rows * T)
         assert float((got - ref).abs().max()) <= 2e-3
         assert abs(float(got.abs().max()) - 1.0) < 1e-6
+
+
+def test_reference_fp32_biquad_amplifies_a_1e7_perturbation_beyond_the_parity_bar():
+    """Why make_inference is pinned to the fp64 restatement of the post-processing and only loosely to the reference's own
+    fp32 lines (inference.py:70-78): torchaudio's sequential fp32 recursion of the 20 Hz biquad (poles at |z| ~ 0.998) is
+    not reproducible below ~5e-4 - perturbing its input by 1e-7 (less than the fp32 noise of ANY two implementations of
+    the network forward, the reference's own CPU and CUDA paths included) moves its output by more than the 1e-4 bar,
+    while the same filter evaluated in fp64 moves by the size of the perturbation.  A bit-faithful fp32 mode (the exact
+    operation order of torchaudio's CPU loop was reconstructed and matches it bit for bit on identical input) therefore
+    cannot bring a GPU forward closer to the reference's post-processed samples than this."""
+    import torchaudio
+    torch.manual_seed(1)
+    x = torch.randn(16, 30000) * 0.2
+    x = x / x.abs().max()
+    x2 = x + 1e-7 * torch.randn_like(x)
+    y, y2 = (torchaudio.functional.highpass_biquad(v, 48000, 20.0) for v in (x, x2))
+    d32 = float((y - y2).abs().max() / y.abs().max())
+    z, z2 = (torchaudio.functional.highpass_biquad(v.double(), 48000, 20.0) for v in (x, x2))
+    d64 = float((z - z2).abs().max() / z.abs().max())
+    assert d32 > 1e-4, d32
+    assert d64 < 2e-6, d64
+    # the reference's fp32 result is itself that far from the exact (fp64) evaluation of its own filter
+    assert 1e-4 < float((y.double() - z).abs().max() / z.abs().max()) < 2e-3
