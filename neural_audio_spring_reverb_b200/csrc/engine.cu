@@ -1341,8 +1341,9 @@ size_t nasr_workspace_bytes(const nasr_engine* e, int B, int64_t T) {
     size_t fit = e->budget_bytes / (per_clip * nplanes);
     if (fit < 1) fit = 1;
     want = per_clip * fit * nplanes;
+    B = (int)fit;
   }
-  return want;
+  return want + partial_bytes(e, B, T);
 }
 
 int64_t nasr_receptive_field(const nasr_engine* e) {
