@@ -312,7 +312,7 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
     t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_cur; t.prof = a.prof;
     err = launch_ring_block(L, s);
   } else if (allow_tc && tc_chain && bs.path == 3) {
-    const int n_grp = ring_groups(e->desc.arch);
+    const int n_grp = ring_groups(e->desc.arch, e->Cp);
     const int pin_ld = 32 * n_grp;
     err = cudaSuccess;
     for (size_t q = 0; q < bs.passes.size() && err == cudaSuccess; ++q) {
@@ -321,7 +321,7 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
       RingLaunch L{};
       L.cache = &e->pass_cache[i][q];
       L.in = a.in; L.in_rows = a.in_rows; L.in_clip_stride_elems = a.in_clip_stride;
-      L.wpacked = ps.w; L.arch = e->desc.arch; L.sm_count = e->sm_count; L.pdl = e->pdl; L.acc = true;
+      L.wpacked = ps.w; L.arch = e->desc.arch; L.sm_count = e->sm_count; L.pdl = e->pdl; L.acc = true; L.cin = e->Cp;
       RingArgs& t = L.a;
       t.in_row0 = a.in_row0 - (long long)ps.tap0 * a.d;   // rows before the plane are the causal zero fill
       t.B = a.B; t.T = a.T; t.k = ps.k; t.d = a.d;
@@ -379,7 +379,7 @@ inline size_t plane_slack_bytes(const nasr_engine* e) { return (size_t)RB_SLACK_
 // fp32 plane of conv sums that the tap passes of a block hand to each other (0 when no block runs in passes)
 inline size_t partial_bytes(const nasr_engine* e, long long clips, long long T) {
   for (const auto& b : e->blocks)
-    if (b.path == 3) return (size_t)clips * T * 128 * ring_groups(e->desc.arch) + plane_slack_bytes(e);
+    if (b.path == 3) return (size_t)clips * T * 128 * ring_groups(e->desc.arch, e->Cp) + plane_slack_bytes(e);
   return 0;
 }
 // ping-pong activation planes of the one-shot forward (a split out_net needs a plane for the last block too)
@@ -465,7 +465,9 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
   {
     const char* env = getenv("NASR_LOWER");
     const bool lower = !(env && atoi(env) == 0);
-    if (lower && desc->path != NASR_PATH_FP32 && e->C >= 16 && e->C < 32) e->Cp = 32;
+    // (a 16-channel GCN / WaveNet needs no padding: the ring kernel has a 16-channel variant with 64-byte rows)
+    const bool native16 = desc->arch == NASR_ARCH_GCN && e->C == 16;
+    if (lower && desc->path != NASR_PATH_FP32 && e->C >= 16 && e->C < 32 && !native16) e->Cp = 32;
   }
   if (const char* env = getenv("NASR_WORKSPACE_MB")) {
     const long long mb = atoll(env);
@@ -628,9 +630,9 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
           for (int j = 0; j < ps.k; ++j) sub[r * ps.k + j] = p_conv[r * k + j0 + j];
         const bool last = q == np - 1;
         std::vector<uint16_t> h_w, part;
-        for (int g = 0; g < ring_groups(desc->arch); ++g) {
+        for (int g = 0; g < ring_groups(desc->arch, Cp); ++g) {
           float isw = 1.f;
-          ring_pack_weights(desc->arch, g, ps.k, sub.data(), last ? p_res.data() : zero_res.data(), part, &isw, &ps.inv_sr, sw);
+          ring_pack_weights(desc->arch, g, ps.k, sub.data(), last ? p_res.data() : zero_res.data(), part, &isw, &ps.inv_sr, sw, 0.f, Cp);
           b.inv_sw = isw;
           h_w.insert(h_w.end(), part.begin(), part.end());
         }

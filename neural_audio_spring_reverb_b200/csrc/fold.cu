@@ -102,11 +102,14 @@ cudaError_t launch_out_net(const float* plane, long long plane_clip_stride, long
                            int B, long long T, int sm_count, cudaStream_t s, unsigned long long* prof) {
   (void)C;
   if (B <= 0 || T <= 0) return cudaSuccess;
-  if (Cp != 32 && Cp != 64) return cudaErrorNotSupported;   // the planes of the ring kernel's GCN variants
+  if (Cp != 16 && Cp != 32 && Cp != 64) return cudaErrorNotSupported;   // the planes of the ring kernel's GCN variants
   long long gx = (T + 255) / 256;               // 8 warps x 32 rows per block and pass
   const long long cap = (long long)sm_count * 8 / B + 1;
   if (gx > cap) gx = cap;
-  if (Cp == 32)
+  if (Cp == 16)
+    out_net_kernel<4><<<dim3((unsigned)gx, B), 256, 0, s>>>(plane, plane_clip_stride, row0, Cp, wout, out_ch, final_tanh, y,
+                                                            y_clip_stride, y_rows, y_row0, T, prof);
+  else if (Cp == 32)
     out_net_kernel<8><<<dim3((unsigned)gx, B), 256, 0, s>>>(plane, plane_clip_stride, row0, Cp, wout, out_ch, final_tanh, y,
                                                             y_clip_stride, y_rows, y_row0, T, prof);
   else

@@ -159,9 +159,11 @@ struct Span {
 
 // ACC: the tap-pass variant (RingArgs::pin / raw_out); a separate instantiation so that the extra registers of the
 // partial-sum rows never touch the plain kernel
-// CIN: input (= output) channels of the block, 32 or 64.  64 (the shipped GCN-3 / GCN-springset shape): a plane row is
+// CIN: input (= output) channels of the block, 16, 32 or 64.  64 (the shipped GCN-3 / GCN-springset shape): a plane row is
 // 256 bytes = [hi 64 ch | lo 64 ch], an input tile two SWIZZLE_128B sub-tiles of 16 KB (hi rows, lo rows), a product
 // term four 16-channel slices, a weight block two 4 KB sub-tiles; the 64 gate channels are four CTA groups of 16.
+// 16 (the shipped WaveNets; GCN only): 64-byte rows = [hi 16 | lo 16], SWIZZLE_64B tiles of 8 KB, one slice per term,
+// one channel group.
 template <int ARCH, bool ACC, int CIN>
 __global__ void __launch_bounds__((4 * RB_ESETS + 2) * 32, 1)
 ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map,
@@ -174,6 +176,8 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
   constexpr int WBLK = CIN * 128;             // bytes of one weight block: 32 rows x CIN x (hi + lo) fp16
   constexpr int KS = CIN / 16;                // 16-channel slices per operand half
   constexpr int NT = 3 * KS;                  // product terms per chunk: xh*wh, xh*wl, xl*wh per slice
+  constexpr int WSUB = CIN == 64 ? 4096 : WBLK;   // bytes of one weight sub-tile (32 rows of min(CIN * 4, 128) bytes)
+  constexpr uint32_t DESC_HI = CIN == 16 ? NASR_DESC_HI_SW64 : NASR_DESC_HI_SW128;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -231,14 +235,14 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
       mbar_arrive_expect_tx(wfull, (uint32_t)(a.NW * WBLK));
       for (int p = 0; p < a.NW; ++p) {
         const int wrow = (grp * NS + (p >= NS ? p - NS : p)) * 32;
-        tma_load_3d(wsm + (size_t)p * 4096, &w_map, wfull, 0, wrow, 0);
+        tma_load_3d(wsm + (size_t)p * WSUB, &w_map, wfull, 0, wrow, 0);
         // 64 channels: the lo halves of all blocks sit behind the hi halves (a chunk of blocks stays contiguous in both)
         if (CIN == 64) tma_load_3d(wsm + (size_t)(a.NW + p) * 4096, &w_map, wfull, 64, wrow, 0);
       }
       // everything above is independent of the previous kernel in the stream
       asm volatile("griddepcontrol.wait;" ::: "memory");
       rb_stamp(a, 2);
-      const uint32_t tile_bytes = (a.mode == 0 ? (uint32_t)(a.G * a.d * 128) : 16384u) * (CIN / 32);
+      const uint32_t tile_bytes = (a.mode == 0 ? (uint32_t)(a.G * a.d * 128) : 16384u) * CIN / 32;
       int st = 0;
       uint32_t empty_phase = ~0u;
       Span s;
@@ -298,12 +302,15 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         if constexpr (CIN == 32) {
           ao = a_off32[c];
           bo = b_off32[c];
+        } else if constexpr (CIN == 16) {   // row = [hi ch 0-15 | lo ch 0-15]
+          ao = c == 2 ? 2u : 0u;
+          bo = c == 1 ? 2u : 0u;
         } else {
           ao = (c >= 2 * KS ? 1024u : 0u) + 2u * (uint32_t)(c % KS);
           bo = ((c >= KS && c < 2 * KS) ? wlo : 0u) + 2u * (uint32_t)(c % KS);
         }
-        const uint64_t da = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (a_lo + ao);
-        const uint64_t db = ((uint64_t)NASR_DESC_HI_SW128 << 32) | (w_lo32 + (uint32_t)b0 * 256u + bo);
+        const uint64_t da = ((uint64_t)DESC_HI << 32) | (a_lo + ao);
+        const uint64_t db = ((uint64_t)DESC_HI << 32) | (w_lo32 + (uint32_t)b0 * (uint32_t)(WSUB >> 4) + bo);
         if (!(a.dbg & 2)) umma_f16(tmem + (uint32_t)(slot * 32), da, db, idesc, acc);
       };
       // steady-state chunks of the slot ring: [0, h0) and [h0, NS)
@@ -807,6 +814,8 @@ bool ring_eligible(int arch, int Cin, int C, int k, int d) {
   if (Cin != C || k < 1 || k + 1 > RB_MAX_SLOTS || d < 1) return false;
   if (C == 64) {   // GCN only; the weights (8 KB per block) must leave room for two input stages
     if (arch != 1 || rb_smem_bytes(k + 1, 2, 64) > 227 * 1024) return false;
+  } else if (C == 16) {   // GCN only (one group of 16 gate channels)
+    if (arch != 1) return false;
   } else if (C != 32) {
     return false;
   }
@@ -869,11 +878,11 @@ static bool make_group_map(CUtensorMap* map, const void* base, uint64_t rext, ui
   if (!enc) return false;
   cuuint64_t dims[4] = {row_elems, rext, jext, clips};
   cuuint64_t strides[3] = {row_elems * 2, S_rows * row_elems * 2, clip_stride_elems * 2};
-  cuuint32_t box[4] = {64, d, G, 1};
+  cuuint32_t box[4] = {row_elems < 64 ? (cuuint32_t)row_elems : 64u, d, G, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             CU_TENSOR_MAP_INTERLEAVE_NONE, row_elems < 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Host-side launch plan (no CUDA calls; unit-tested on the CPU through nasr_debug_ring_plan): walk mode, span length,
@@ -997,7 +1006,7 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   RingMapCache local;
   RingMapCache* c = L.cache ? L.cache : &local;
   const int cin = L.cin;
-  if (cin != 32 && !(cin == 64 && L.arch == 1 && !L.acc)) return cudaErrorInvalidConfiguration;
+  if (cin != 32 && !(cin == 64 && L.arch == 1 && !L.acc) && !(cin == 16 && L.arch == 1)) return cudaErrorInvalidConfiguration;
   const int n_grp = ring_groups(L.arch, cin);
   long long grid = 0;
   {
@@ -1063,10 +1072,11 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   }
 
   cudaError_t err;
-  static unsigned long long attr_set[5] = {0, 0, 0, 0, 0};
+  static unsigned long long attr_set[7] = {0, 0, 0, 0, 0, 0, 0};
   const void* fn;
   int fi;
   if (cin == 64) { fn = (const void*)ring_block_kernel<1, false, 64>; fi = 4; }
+  else if (cin == 16) { fn = L.acc ? (const void*)ring_block_kernel<1, true, 16> : (const void*)ring_block_kernel<1, false, 16>; fi = L.acc ? 6 : 5; }
   else if (L.arch == 0) { fn = L.acc ? (const void*)ring_block_kernel<0, true, 32> : (const void*)ring_block_kernel<0, false, 32>; fi = L.acc ? 2 : 0; }
   else { fn = L.acc ? (const void*)ring_block_kernel<1, true, 32> : (const void*)ring_block_kernel<1, false, 32>; fi = L.acc ? 3 : 1; }
   if (attr_needed_on_this_device(attr_set[fi])) {
@@ -1084,6 +1094,8 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   cfg.attrs = at;
   cfg.numAttrs = L.pdl ? 1 : 0;
   if (cin == 64) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<1, false, 64>, in_map, w_map, out_map, a);
+  else if (cin == 16 && L.acc) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<1, true, 16>, in_map, w_map, out_map, a);
+  else if (cin == 16) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<1, false, 16>, in_map, w_map, out_map, a);
   else if (L.arch == 0 && !L.acc) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<0, false, 32>, in_map, w_map, out_map, a);
   else if (L.arch == 0) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<0, true, 32>, in_map, w_map, out_map, a);
   else if (!L.acc) err = cudaLaunchKernelEx(&cfg, ring_block_kernel<1, false, 32>, in_map, w_map, out_map, a);

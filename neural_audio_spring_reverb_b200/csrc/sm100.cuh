@@ -159,6 +159,8 @@ __device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint
 }
 // K-major SWIZZLE_128B descriptor high word: SBO = 1024 B, version 1, layout type 2
 #define NASR_DESC_HI_SW128 0x40004040
+// K-major SWIZZLE_64B (64-byte rows, 8-row groups 512 B apart): SBO = 512 B, version 1, layout type 4
+#define NASR_DESC_HI_SW64 0x80004020
 // Variant with the descriptor high word and the instruction descriptor as immediates (they
 // then live in uniform registers for free) and a per-lane predicate: exactly one lane of the
 // (converged) warp passes pred != 0 and its a_lo / b_lo / tmem_d / accumulate are used.
@@ -209,17 +211,18 @@ inline PFN_encodeTiled get_encode_tiled() {
 
 // 16-bit plane [clips][rows][row_elems] (row_elems * 2 bytes = 128-byte multiple),
 // box = [64 elems (128 B)][box_rows][1], SWIZZLE_128B, out-of-range rows read as zero.
+// (rows of 32 elements = 64 bytes: box = [32 elems][box_rows][1], SWIZZLE_64B.)
 inline bool make_plane_map(CUtensorMap* map, const void* base, uint64_t row_elems, uint64_t rows, uint64_t clips,
                            uint64_t clip_stride_elems, uint32_t box_rows) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
   cuuint64_t dims[3] = {row_elems, rows, clips};
   cuuint64_t strides[2] = {row_elems * 2, clip_stride_elems * 2};
-  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t box[3] = {row_elems < 64 ? (cuuint32_t)row_elems : 64u, box_rows, 1};
   cuuint32_t es[3] = {1, 1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             CU_TENSOR_MAP_INTERLEAVE_NONE, row_elems < 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace nasr

@@ -461,11 +461,26 @@ WIDE_SHAPES = [
 ]
 
 
+NARROW_SHAPES = [
+    # GCN / WaveNet with 16 channels: 64-byte plane rows, SWIZZLE_64B tiles, one channel group
+    (4, 3, 10), (3, 5, 7), (3, 15, 2), (3, 2, 200), (2, 1, 3),
+]
+
+
+@pytest.mark.parametrize("n_blocks,k,g", NARROW_SHAPES)
+def test_gcn_16_channels_on_the_ring_kernel(n_blocks, k, g):
+    _gcn_width_case(16, n_blocks, k, g)
+
+
 @pytest.mark.parametrize("n_blocks,k,g", WIDE_SHAPES)
 def test_gcn_64_channels_on_the_ring_kernel(n_blocks, k, g):
+    _gcn_width_case(64, n_blocks, k, g)
+
+
+def _gcn_width_case(C, n_blocks, k, g):
     import neural_audio_spring_reverb_b200 as N
-    cfg = dict(arch="GCN", n_blocks=n_blocks, n_channels=64, kernel_size=k, dilation_growth=g, cond_dim=2)
-    sd = O.build_state("GCN", n_blocks, 64, k, 2, seed=64 + k + g)
+    cfg = dict(arch="GCN", n_blocks=n_blocks, n_channels=C, kernel_size=k, dilation_growth=g, cond_dim=2)
+    sd = O.build_state("GCN", n_blocks, C, k, 2, seed=C + k + g)
     dil = [g ** i for i in range(n_blocks)]
     m = build_model(cfg, sd, DEV)
     assert [m._engine().block_path(i) for i in range(n_blocks)] == [0] + [2] * (n_blocks - 1)
