@@ -460,7 +460,7 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
   e->sm_count = prop.multiProcessorCount;
   e->C = desc->n_channels;
   e->Cp = round_up(desc->n_channels, 4);
-  // 16 .. 31 channels (the shipped WaveNets, BASELINE config 1): planes and weights are padded to 32 channels with
+  // 16 .. 31 channels (BASELINE config 1 = a TCN with 16 channels): planes and weights are padded to 32 channels with
   // zeros, so that the blocks run on the 32-channel tensor-core kernels (NASR_LOWER=0: fp32 FFMA kernels as before)
   {
     const char* env = getenv("NASR_LOWER");
