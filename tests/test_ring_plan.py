@@ -76,6 +76,10 @@ CASES = [
     (0, 15, 4, 1, 1, 0), (0, 15, 4, 3, 127, 0), (0, 2, 100, 1, 3000, 0), (0, 9, 127, 1, 5000, 0),
     (0, 15, 16, 1, 1024, 14 * 16), (0, 15, 256, 2, 777, 14 * 256), (0, 5, 32, 1, 65536, 4 * 32),
     (0, 15, 2, 1, 480000, 0), (0, 15, 512, 8, 480000, 0),
+    # tap passes (engine.cu path 3): pass p of a k = 99 block reads the plane 15 p d rows earlier - a NEGATIVE in_row0 in
+    # a one-shot forward (rows before the plane = causal zero fill), history rows (in_row0 = 98 d - 15 p d) in a stream
+    (0, 15, 14, 1, 9000, -15 * 14), (0, 9, 14, 2, 9000, -90 * 14), (1, 15, 2, 1, 5000, -30), (0, 15, 512, 1, 30000, -45 * 512),
+    (0, 15, 1, 1, 3000, -90), (0, 15, 16, 1, 1024, 98 * 16 - 45 * 16), (1, 9, 10, 1, 4099, 98 * 10 - 90 * 10),
 ]
 
 
@@ -90,7 +94,7 @@ def test_plan_covers_every_sample_once(arch, k, d, B, T, in_row0):
     if T * B > 2_000_000:        # the replay is O(samples) in numpy: only the plan's invariants at full size
         assert p["total_spans"] >= p["grid"] // p["n_grp"]
         return
-    in_rows = in_row0 + T
+    in_rows = max(in_row0, 0) + T
     written, max_row = replay(p, k, d, B, T, in_row0, in_rows)
     assert written.min() == 1 and written.max() == 1
     assert max_row < in_rows + RB_SLACK_ROWS        # over-read stays inside the plane's slack
