@@ -59,6 +59,7 @@ struct BlockState {
     float inv_sr = 1.f;
   };
   std::vector<TapPass> passes;
+  int pass_taps = 0;   // taps of the largest pass
 };
 
 constexpr int kPassTaps = RB_MAX_SLOTS - 1;   // taps per pass: the ring's slots minus the residual slot
@@ -312,9 +313,21 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
     t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_cur; t.prof = a.prof;
     err = launch_ring_block(L, s);
   } else if (allow_tc && tc_chain && bs.path == 3) {
-    const int n_grp = ring_groups(e->desc.arch, e->Cp);
-    const int pin_ld = 32 * n_grp;
-    err = cudaSuccess;
+    // one span plan for every pass of the block (the partial plane is laid out by it)
+    long long pass_n = 0;
+    const size_t need = ring_pass_plan(e->desc.arch, e->Cp, e->sm_count, bs.pass_taps, a.d, a.B, a.T, a.in_row0, &pass_n);
+    err = need == 0 ? cudaErrorInvalidConfiguration : cudaSuccess;
+    if (err == cudaSuccess && need > e->partial.cap) {
+      // a slice of another size than the one the plane was sized for (its plan may pad differently): grow, unless this
+      // launch is being captured into a chunk graph (those shapes are sized before the capture)
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(s, &cs);
+      if (cs != cudaStreamCaptureStatusNone) err = cudaErrorInvalidConfiguration;
+      else {
+        err = cudaStreamSynchronize(s);
+        if (err == cudaSuccess) err = ensure(e->partial, need + 4096);
+      }
+    }
     for (size_t q = 0; q < bs.passes.size() && err == cudaSuccess; ++q) {
       const BlockState::TapPass& ps = bs.passes[q];
       const bool last = q + 1 == bs.passes.size();
@@ -322,6 +335,7 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
       L.cache = &e->pass_cache[i][q];
       L.in = a.in; L.in_rows = a.in_rows; L.in_clip_stride_elems = a.in_clip_stride;
       L.wpacked = ps.w; L.arch = e->desc.arch; L.sm_count = e->sm_count; L.pdl = e->pdl; L.acc = true; L.cin = e->Cp;
+      L.force_n = pass_n;
       RingArgs& t = L.a;
       t.in_row0 = a.in_row0 - (long long)ps.tap0 * a.d;   // rows before the plane are the causal zero fill
       t.B = a.B; t.T = a.T; t.k = ps.k; t.d = a.d;
@@ -329,14 +343,12 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
       t.inv_sw = bs.inv_sw * kActInv; t.inv_sr = ps.inv_sr * kActInv;
       t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_cur; t.prof = a.prof;
       t.pin = q > 0 ? (const float*)e->partial.p : nullptr;
-      t.pin_clip_stride = a.T * pin_ld; t.pin_ld = pin_ld;
       if (last) {
         t.out = a.out; t.out_fmt = a.out_fmt; t.out_clip_stride = a.out_clip_stride; t.out_rows = a.out_rows;
         t.out_row0 = a.out_row0;
       } else {
         t.raw_out = 1;
-        t.out = e->partial.p; t.out_fmt = FMT_CL; t.out_clip_stride = a.T * pin_ld; t.out_rows = a.T; t.out_row0 = 0;
-        t.out_row_bytes = pin_ld * 4;
+        t.out = e->partial.p; t.out_fmt = FMT_CL; t.out_clip_stride = 0; t.out_rows = a.T; t.out_row0 = 0;
       }
       err = launch_ring_block(L, s);
       if (err == cudaSuccess && !last) e->launches += 1;
@@ -376,11 +388,16 @@ inline size_t plane_row_bytes(const nasr_engine* e) { return (size_t)e->Cp * 4; 
 // tail slack of every activation plane: the ring kernel's grouped TMA view may read (never use) rows past
 // the last clip (ring_block.cuh)
 inline size_t plane_slack_bytes(const nasr_engine* e) { return (size_t)RB_SLACK_ROWS * (e->Cp > 32 ? e->Cp * 4 : 128); }
-// fp32 plane of conv sums that the tap passes of a block hand to each other (0 when no block runs in passes)
-inline size_t partial_bytes(const nasr_engine* e, long long clips, long long T) {
-  for (const auto& b : e->blocks)
-    if (b.path == 3) return (size_t)clips * T * 128 * ring_groups(e->desc.arch, e->Cp) + plane_slack_bytes(e);
-  return 0;
+// fp32 plane of conv sums that the tap passes of a block hand to each other (0 when no block runs in passes): laid out by
+// the span plan the passes share, so its size comes from that plan (in_row0 = the block's history rows in a stream)
+inline size_t partial_bytes(const nasr_engine* e, long long clips, long long T, bool streaming = false) {
+  size_t need = 0;
+  for (const auto& b : e->blocks) {
+    if (b.path != 3) continue;
+    const size_t q = ring_pass_plan(e->desc.arch, e->Cp, e->sm_count, b.pass_taps, b.d, (int)clips, T, streaming ? b.hist : 0, nullptr);
+    if (q > need) need = q;
+  }
+  return need ? need + 4096 : 0;
 }
 // ping-pong activation planes of the one-shot forward (a split out_net needs a plane for the last block too)
 inline int planes_needed(const nasr_engine* e) {
@@ -620,6 +637,7 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
       const std::vector<float> zero_res((size_t)Cp * b.Cinp, 0.f);
       const int np = (k + pass_taps - 1) / pass_taps;
       e->pass_cache[i].resize(np);
+      b.pass_taps = pass_taps;
       for (int q = 0; q < np; ++q) {
         BlockState::TapPass ps;
         ps.tap0 = (np - 1 - q) * pass_taps;
@@ -1246,7 +1264,7 @@ int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev, int B, 
       need_scratch += (segs * bs.hist * ((i == 0) ? 4 : (size_t)rb) + 15) & ~(size_t)15;
     }
     const size_t need_y = (size_t)B * e->desc.out_ch * Tc * sizeof(float);
-    const size_t need_partial = partial_bytes(e, B, Tc);
+    const size_t need_partial = partial_bytes(e, B, Tc, true);
     if (e->sfinal.cap < need_final || e->scratch.cap < need_scratch || e->ychunk.cap < need_y || e->partial.cap < need_partial) {
       NASR_CUDA(e, cudaStreamSynchronize(s));
       drop_chunk_graphs(e);

@@ -557,30 +557,28 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         const bool zero_c = (a.dbg & 256) || i + 1 < s.nsteps;
         const bool zero_r = (a.dbg & 256) || (s.nsteps - 2 - i >= km1);
         uint64_t* drained_e = &drained[e & 1u];
-        // tap passes: this row's conv sums of the earlier passes (issued before the wait: the address is known)
-        uint4 pv[ACC ? 8 : 1];
+        // tap passes: the conv sums of the earlier passes, fetched before the wait (the addresses are known).  Every pass of
+        // a block runs the same span plan, so a (span, step, group, warp) owns one 4 KB block of the partial plane, stored
+        // [32 columns][32 lanes]: a warp reads / writes one 128-byte line per instruction (a thread's own 128-byte row
+        // would cost 32 LSU wavefronts per instruction)
+        uint32_t pv[ACC ? 32 : 1];
+        const long long pblk = ACC ? ((((long long)sp * a.n + i) * n_grp + grp) * 4 + quad) * 1024 + lane : 0;
         if (ACC && a.pin) {
-          const long long t = t0 + off;
-          if (ok && t < a.T) {
-            const uint4* pp = reinterpret_cast<const uint4*>(a.pin + (long long)s.b * a.pin_clip_stride + t * a.pin_ld + grp * 32);
 #pragma unroll
-            for (int q = 0; q < (ACC ? 8 : 1); ++q)
-              asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pv[q].x), "=r"(pv[q].y), "=r"(pv[q].z), "=r"(pv[q].w) : "l"(pp + q) : "memory");
-          } else {
-#pragma unroll
-            for (int q = 0; q < (ACC ? 8 : 1); ++q) pv[q] = make_uint4(0u, 0u, 0u, 0u);
-          }
+          for (int c = 0; c < (ACC ? 32 : 1); ++c)
+            asm volatile("ld.global.u32 %0, [%1];" : "=r"(pv[c]) : "l"(a.pin + pblk + c * 32) : "memory");
         }
         auto add_pin = [&](uint32_t (&u)[32]) {
           if (ACC && a.pin) {
 #pragma unroll
-            for (int q = 0; q < (ACC ? 8 : 1); ++q) {
-              u[4 * q] = __float_as_uint(__uint_as_float(u[4 * q]) + __uint_as_float(pv[q].x));
-              u[4 * q + 1] = __float_as_uint(__uint_as_float(u[4 * q + 1]) + __uint_as_float(pv[q].y));
-              u[4 * q + 2] = __float_as_uint(__uint_as_float(u[4 * q + 2]) + __uint_as_float(pv[q].z));
-              u[4 * q + 3] = __float_as_uint(__uint_as_float(u[4 * q + 3]) + __uint_as_float(pv[q].w));
-            }
+            for (int c = 0; c < (ACC ? 32 : 1); ++c) u[c] = __float_as_uint(__uint_as_float(u[c]) + __uint_as_float(pv[c]));
           }
+        };
+        // a pass that is not the block's last hands the raw conv sums (+ pin) on in the same layout
+        auto put_raw = [&](const uint32_t (&u)[32]) {
+          float* ob = reinterpret_cast<float*>(a.out) + pblk;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) asm volatile("st.global.u32 [%0], %1;" ::"l"(ob + c * 32), "r"(u[c]) : "memory");
         };
         // coalesced stores of the staged rows: NCH lanes per row, chunk my_c of the row at byte cb
         auto store_rows = [&](int cb) {
@@ -672,13 +670,12 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           if (lane == 0) mbar_arrive(drained_e);
           if (quad == 0 && lane == 0 && sp == sp0) rb_step_stamp(a, 1, i + km1);
           add_pin(u);
+          if (ACC && a.raw_out) {
+            put_raw(u);
+            continue;
+          }
           // 4 channels: affine -> PReLU -> + residual
           auto out4 = [&](int c, float (&o4)[4]) {
-            if (ACC && a.raw_out) {   // tap pass that is not the block's last: hand the raw conv sums on
-              o4[0] = __uint_as_float(u[c]); o4[1] = __uint_as_float(u[c + 1]);
-              o4[2] = __uint_as_float(u[c + 2]); o4[3] = __uint_as_float(u[c + 3]);
-              return;
-            }
             const float4 s4 = *reinterpret_cast<const float4*>(aff + c);
             const float4 h4 = *reinterpret_cast<const float4*>(aff + 32 + c);
             const float2 y0 = __ffma2_rn(make_float2(__uint_as_float(u[c]), __uint_as_float(u[c + 1])), make_float2(s4.x, s4.y),
@@ -741,17 +738,8 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           if (lane == 0) mbar_arrive(drained_e);
           if (a.out_fmt == FMT_FINAL) continue;   // not produced by the GCN groups (engine: split out_net)
           add_pin(u);
-          if (ACC && a.raw_out) {   // raw conv sums of this group: 32 floats = two staged rounds of 16
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              float o[16];
-#pragma unroll
-              for (int c = 0; c < 16; ++c) o[c] = __uint_as_float(u[16 * r + c]);
-              stage16(o, 0, 2);
-              __syncwarp();
-              store_rows(grp * 128 + r * 64 + my_c * 16);
-              __syncwarp();
-            }
+          if (ACC && a.raw_out) {
+            put_raw(u);
             continue;
           }
           float o[16];
@@ -946,6 +934,16 @@ cudaError_t ring_plan(int arch, int sm_count, long long cached_n, RingArgs& a, l
   return cudaSuccess;
 }
 
+size_t ring_pass_plan(int arch, int cin, int sm_count, int k_pass, int d, int B, long long T, long long in_row0, long long* n_out) {
+  RingArgs a{};
+  a.B = B; a.T = T; a.k = k_pass; a.d = d; a.in_row0 = in_row0;
+  long long grid = 0;
+  if (B <= 0 || T <= 0 || ring_plan(arch, sm_count, 0, a, &grid, cin) != cudaSuccess) return 0;
+  if (n_out) *n_out = a.n;
+  // one 4 KB block per (span, step, channel group, epilogue warp)
+  return (size_t)a.total_spans * (size_t)a.n * (size_t)a.n_grp * 4 * 4096;
+}
+
 // dev / tests: the plan as plain integers {mode, G, L, n, S, NP, spans_per_strip, total_spans, grid, stages, NS, NW,
 // tmem_cols, smem_bytes, n_grp, rext(mode S), jext is per plane}; returns 0 on success
 int ring_debug_plan(int arch, int k, int d, int B, long long T, long long in_row0, int sm_count, long long* out16) {
@@ -1011,10 +1009,12 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   long long grid = 0;
   {
     long long cached_n = 0;
-    if (c->n_B == a.B && c->n_T == a.T && c->n_d == a.d && c->n_k == a.k && c->n_row0 == a.in_row0 && c->n_sm == L.sm_count)
+    if (L.force_n > 0) cached_n = L.force_n;
+    else if (c->n_B == a.B && c->n_T == a.T && c->n_d == a.d && c->n_k == a.k && c->n_row0 == a.in_row0 && c->n_sm == L.sm_count)
       cached_n = c->n;
     cudaError_t perr = ring_plan(L.arch, L.sm_count, cached_n, a, &grid, cin);
     if (perr != cudaSuccess) return perr;
+    if (L.force_n > 0 && a.n != L.force_n) return cudaErrorInvalidConfiguration;   // tap passes must share one span plan
     c->n_B = a.B; c->n_T = a.T; c->n_d = a.d; c->n_k = a.k; c->n_row0 = a.in_row0; c->n_sm = L.sm_count; c->n = a.n;
   }
   const size_t smem = rb_smem_bytes(a.NS, a.stages, cin);

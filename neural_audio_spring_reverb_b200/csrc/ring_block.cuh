@@ -42,10 +42,9 @@ struct RingArgs {
   unsigned int* sat_flag;
   int tma_out;             // rows leave through TMA stores of the staging tiles where the geometry allows
   // tap passes (k > 15, engine.cu): a block's taps are split over several launches of this kernel that hand the conv
-  // sums on through an fp32 plane [B][T][pin_ld] (32 floats per channel group: the raw accumulator columns)
+  // sums on through an fp32 plane.  All passes of a block run the same span plan (RingLaunch::force_n); the plane holds one
+  // 4 KB block [32 accumulator columns][32 lanes] per (span, step, channel group, warp)
   const float* pin;        // partial sums of the earlier passes, added to the conv accumulators, or NULL
-  long long pin_clip_stride;   // floats between clips
-  int pin_ld;              // floats per row (32 * n_grp)
   int raw_out;             // 1: write the raw conv sums (+ pin) to `out` (same layout as pin) instead of the block's output
   int out_row_bytes;       // bytes per output plane row (0 = 4 bytes per channel of the block)
   int l2_prefetch;         // > 0: TMA-prefetch the input tile of that many steps ahead into L2
@@ -79,7 +78,8 @@ struct RingLaunch {
   int arch, sm_count;
   bool pdl = false;                 // programmatic dependent launch (prologue overlaps the previous kernel's tail)
   bool acc = false;                 // tap-pass variant of the kernel (a.pin / a.raw_out honoured)
-  int cin = 32;                     // channels of the block (32, or 64 for GCN): plane rows are cin * 4 bytes
+  int cin = 32;                     // channels of the block (32, or 64 / 16 for GCN): plane rows are cin * 4 bytes
+  long long force_n = 0;            // tap passes: steps per span every pass of the block must use (ring_pass_plan)
   RingArgs a;
 };
 
@@ -93,6 +93,9 @@ int ring_groups(int arch, int C = 32);
 void ring_pack_weights(int arch, int grp, int k, const float* conv_w, const float* res_w, std::vector<uint16_t>& out,
                        float* inv_sw, float* inv_sr, float force_sw = 0.f, float force_sr = 0.f, int C = 32);
 float ring_weight_scale(const float* w, size_t n);
+// tap passes: the span plan all passes of a block share (planned for the pass with the most taps and the unshifted input)
+// and the bytes of the partial plane it needs; 0 on failure
+size_t ring_pass_plan(int arch, int cin, int sm_count, int k_pass, int d, int B, long long T, long long in_row0, long long* n_out);
 cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s);
 int ring_debug_stamps(unsigned long long* host, int max_ctas);
 int ring_debug_steps(unsigned long long* host);
