@@ -74,7 +74,9 @@ struct nasr_engine {
   std::vector<TcMapCache> tc_cache;   // per block: last TMA descriptors
   std::vector<RingMapCache> ring_cache;
   std::vector<std::vector<RingMapCache>> pass_cache;   // [block][pass]
-  DevBuf partial;   // tap passes: fp32 conv sums [clips][T][32 * groups]
+  DevBuf partial;   // tap passes: fp32 conv sums, laid out by the passes' span plan
+  DevBuf xch;       // GCN, 32 channels, out_net fused into the last ring block: the word per output sample in which the two
+                    // channel groups exchange their halves of the dot product (all ones before every forward)
   ToepMapCache toep_cache;
   float* wout = nullptr;  // [out_ch][Cp]
   FoldArgs* fold_dev = nullptr;
@@ -311,6 +313,7 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
     t.scale = a.scale; t.shift = a.shift; t.ld_affine = bs.Wp; t.slope = a.slope;
     t.inv_sw = bs.inv_sw * kActInv; t.inv_sr = bs.inv_sr * kActInv;   // the input plane holds value * kActScale
     t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_cur; t.prof = a.prof;
+    t.xch = (unsigned int*)e->xch.p;
     err = launch_ring_block(L, s);
   } else if (allow_tc && tc_chain && bs.path == 3) {
     // one span plan for every pass of the block (the partial plane is laid out by it)
@@ -342,6 +345,7 @@ int launch_block(nasr_engine* e, const BlockArgs& a, int i, cudaStream_t s, bool
       t.scale = a.scale; t.shift = a.shift; t.ld_affine = bs.Wp; t.slope = a.slope;
       t.inv_sw = bs.inv_sw * kActInv; t.inv_sr = ps.inv_sr * kActInv;
       t.wout = a.wout; t.out_ch = a.out_ch; t.final_tanh = a.final_tanh; t.sat_flag = e->sat_cur; t.prof = a.prof;
+      t.xch = (unsigned int*)e->xch.p;
       t.pin = q > 0 ? (const float*)e->partial.p : nullptr;
       if (last) {
         t.out = a.out; t.out_fmt = a.out_fmt; t.out_clip_stride = a.out_clip_stride; t.out_rows = a.out_rows;
@@ -399,6 +403,13 @@ inline size_t partial_bytes(const nasr_engine* e, long long clips, long long T, 
   }
   return need ? need + 4096 : 0;
 }
+// exchange words of the fused GCN out_net (two channel groups): one per output sample of a launch, 0 when not needed
+inline size_t xch_bytes(const nasr_engine* e, long long clips, long long T) {
+  const BlockState& last = e->blocks.back();
+  const bool need = e->desc.arch == NASR_ARCH_GCN && (last.path == 2 || last.path == 3) && !last.split_out &&
+                    ring_groups(e->desc.arch, e->Cp) == 2;
+  return need ? (size_t)clips * e->desc.out_ch * T * sizeof(unsigned int) : 0;
+}
 // ping-pong activation planes of the one-shot forward (a split out_net needs a plane for the last block too)
 inline int planes_needed(const nasr_engine* e) {
   const int n = (int)e->blocks.size();
@@ -434,6 +445,7 @@ void nasr_engine_destroy(nasr_engine* e) {
     release(e->plane[0]); release(e->plane[1]);
     for (auto& p : e->splane) release(p);
     release(e->partial);
+    release(e->xch);
     release(e->scratch); release(e->sfinal); release(e->hx); release(e->hy); release(e->hc); release(e->ychunk);
     for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (int q = 0; q < 2; ++q) {
@@ -546,7 +558,9 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
     b.path = path_of(i);
     b.in_fmt = (i == 0) ? FMT_NCT : (b.path != 0 ? FMT_SPLIT16 : FMT_CL);
     b.out_fmt = (i == n - 1) ? FMT_FINAL : (path_of(i + 1) != 0 ? FMT_SPLIT16 : FMT_CL);
-    b.split_out = gcn && i == n - 1 && (b.path == 2 || b.path == 3);
+    // (16 channels = one group: out_net is row-local; 32 channels = two groups: they meet through nasr_engine::xch; the four
+    // groups of 64 channels keep the separate kernel)
+    b.split_out = gcn && i == n - 1 && (b.path == 2 || b.path == 3) && Cp == 64;
     if (b.split_out) b.out_fmt = FMT_CL;
     if (b.Wp / b.NC > 16) { rc = fail(nullptr, NASR_ERR_INVALID, "channel count too large for the generic kernel"); break; }
 
@@ -762,6 +776,10 @@ static int forward_slice(nasr_engine* e, const float* x, float* y, int b0, int B
   const int n = (int)e->blocks.size();
   const size_t row_bytes = plane_row_bytes(e);
   const long long plane_elems = (long long)T * e->Cp;  // fp32 elements per clip
+  if (tc) {   // first thing in the stream, so that it does not sit between two programmatically dependent kernels
+    const size_t xb = xch_bytes(e, B, T);
+    if (xb) NASR_CUDA(e, cudaMemsetAsync(e->xch.p, 0xFF, xb, s));
+  }
   for (int i = 0; i < n; ++i) {
     const BlockState& bs = e->blocks[i];
     BlockArgs a = make_args(e, i, B, tc);
@@ -820,10 +838,11 @@ static int ensure_planes(nasr_engine* e, int want, int64_t T, cudaStream_t s, in
       }
     }
   }
-  const size_t need_partial = partial_bytes(e, *slice, T);
-  if (e->partial.cap < need_partial) {
+  const size_t need_partial = partial_bytes(e, *slice, T), need_xch = xch_bytes(e, *slice, T);
+  if (e->partial.cap < need_partial || e->xch.cap < need_xch) {
     NASR_CUDA(e, cudaStreamSynchronize(s));
     NASR_CUDA(e, ensure(e->partial, need_partial));
+    NASR_CUDA(e, ensure(e->xch, need_xch));
   }
   return NASR_OK;
 }
@@ -1161,6 +1180,7 @@ static void drop_chunk_graphs(nasr_engine* e) {
 // carry.  Everything it touches is engine-owned and allocated beforehand, so the sequence can be captured into a graph.
 static int chunk_body(nasr_engine* e, float* y_out, int B, int64_t Tc, cudaStream_t s) {
   const int n = (int)e->blocks.size();
+  if (const size_t xb = xch_bytes(e, B, Tc)) NASR_CUDA(e, cudaMemsetAsync(e->xch.p, 0xFF, xb, s));
   const long long Tcap = e->streamTcap;
   const long long rb = (long long)plane_row_bytes(e);
   const int in_ch = e->desc.in_ch;
@@ -1264,14 +1284,16 @@ int nasr_forward_chunk(nasr_engine* e, const float* x_dev, float* y_dev, int B, 
       need_scratch += (segs * bs.hist * ((i == 0) ? 4 : (size_t)rb) + 15) & ~(size_t)15;
     }
     const size_t need_y = (size_t)B * e->desc.out_ch * Tc * sizeof(float);
-    const size_t need_partial = partial_bytes(e, B, Tc, true);
-    if (e->sfinal.cap < need_final || e->scratch.cap < need_scratch || e->ychunk.cap < need_y || e->partial.cap < need_partial) {
+    const size_t need_partial = partial_bytes(e, B, Tc, true), need_xch = xch_bytes(e, B, Tc);
+    if (e->sfinal.cap < need_final || e->scratch.cap < need_scratch || e->ychunk.cap < need_y || e->partial.cap < need_partial ||
+        e->xch.cap < need_xch) {
       NASR_CUDA(e, cudaStreamSynchronize(s));
       drop_chunk_graphs(e);
       NASR_CUDA(e, ensure(e->sfinal, need_final));
       NASR_CUDA(e, ensure(e->scratch, need_scratch));
       NASR_CUDA(e, ensure(e->ychunk, need_y));
       NASR_CUDA(e, ensure(e->partial, need_partial));
+      NASR_CUDA(e, ensure(e->xch, need_xch));
     }
   }
   sat_stream(e);

@@ -736,7 +736,6 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(drained_e);
-          if (a.out_fmt == FMT_FINAL) continue;   // not produced by the GCN groups (engine: split out_net)
           add_pin(u);
           if (ACC && a.raw_out) {
             put_raw(u);
@@ -748,6 +747,30 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             const float yt = fmaf(__uint_as_float(u[c]), aff[c], aff[32 + c]);
             const float ys = fmaf(__uint_as_float(u[16 + c]), aff[16 + c], aff[48 + c]);
             o[c] = fmaf(__uint_as_float(v[c]), inv_sr, rb_tanh(yt) * rb_sigmoid(ys) * oscale);
+          }
+          if (a.out_fmt == FMT_FINAL) {
+            // out_net 1x1 (+ tanh), gcn.py:145-146.  One channel group (16 channels): row-local.  Two groups (32 channels):
+            // each CTA has half of the dot product; the halves meet in a word per output sample that the engine pre-fills
+            // with an all-ones pattern: atomicExch leaves this group's half there, and whoever gets the OTHER group's half
+            // back (instead of the pattern) adds the two - a + b is the same in either order - and writes the sample
+            const long long t = t0 + off;
+            const bool valid = ok && t < a.T;
+            for (int oc = 0; oc < a.out_ch; ++oc) {
+              const float* wv = a.wout + oc * CIN + grp * 16;
+              float y = 0.f;
+#pragma unroll
+              for (int c = 0; c < 16; ++c) y = fmaf(o[c], __ldg(wv + c), y);
+              if (!valid) continue;
+              const long long idx = ((long long)s.b * a.out_ch + oc) * a.T + t;
+              if (n_grp == 2) {
+                const uint32_t other = atomicExch(a.xch + idx, __float_as_uint(y));
+                if (other == 0xFFFFFFFFu) continue;
+                y += __uint_as_float(other);
+              }
+              if (a.final_tanh) y = tanhf(y);
+              ((float*)a.out)[(long long)s.b * a.out_clip_stride + (long long)oc * a.out_rows + a.out_row0 + t] = y;
+            }
+            continue;
           }
           stage16(o, 0, 2);   // staged group row: [hi 16 ch (chunks 0-1) | lo 16 ch (chunks 2-3)] or 4 fp32 chunks
         }
@@ -982,6 +1005,10 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   if (a.B <= 0 || a.T <= 0) return cudaSuccess;
   if (a.out_row_bytes <= 0) a.out_row_bytes = L.cin * 4;
   if (!L.acc && (a.pin || a.raw_out)) return cudaErrorInvalidValue;
+  if (L.arch == 1 && a.out_fmt == FMT_FINAL) {   // fused out_net: one group, or two groups meeting in a.xch
+    const int g = ring_groups(L.arch, L.cin);
+    if (g > 2 || (g == 2 && !a.xch)) return cudaErrorInvalidValue;
+  }
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("NASR_RB_DBG"); dbg = e ? atoi(e) : 0; }
