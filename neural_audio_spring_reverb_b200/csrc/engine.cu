@@ -406,9 +406,9 @@ inline size_t partial_bytes(const nasr_engine* e, long long clips, long long T, 
 // exchange words of the fused GCN out_net (two channel groups): one per output sample of a launch, 0 when not needed
 inline size_t xch_bytes(const nasr_engine* e, long long clips, long long T) {
   const BlockState& last = e->blocks.back();
-  const bool need = e->desc.arch == NASR_ARCH_GCN && (last.path == 2 || last.path == 3) && !last.split_out &&
-                    ring_groups(e->desc.arch, e->Cp) == 2;
-  return need ? (size_t)clips * e->desc.out_ch * T * sizeof(unsigned int) : 0;
+  const int g = ring_groups(e->desc.arch, e->Cp);
+  const bool need = e->desc.arch == NASR_ARCH_GCN && (last.path == 2 || last.path == 3) && !last.split_out && g >= 2;
+  return need ? (size_t)clips * e->desc.out_ch * T * sizeof(unsigned int) * (g == 4 ? 3 : 1) : 0;
 }
 // ping-pong activation planes of the one-shot forward (a split out_net needs a plane for the last block too)
 inline int planes_needed(const nasr_engine* e) {
@@ -558,9 +558,9 @@ int nasr_engine_create(const nasr_model_desc* desc, const float* w, size_t n_wei
     b.path = path_of(i);
     b.in_fmt = (i == 0) ? FMT_NCT : (b.path != 0 ? FMT_SPLIT16 : FMT_CL);
     b.out_fmt = (i == n - 1) ? FMT_FINAL : (path_of(i + 1) != 0 ? FMT_SPLIT16 : FMT_CL);
-    // (16 channels = one group: out_net is row-local; 32 channels = two groups: they meet through nasr_engine::xch; the four
-    // groups of 64 channels keep the separate kernel)
-    b.split_out = gcn && i == n - 1 && (b.path == 2 || b.path == 3) && Cp == 64;
+    // (16 channels = one group: out_net is row-local; 32 / 64 channels = two / four groups: they meet through nasr_engine::xch)
+    b.split_out = false;   // (kept for NASR_SPLIT_OUT=1, dev: the separate out_net kernel behind the last GCN ring block)
+    if (const char* env = getenv("NASR_SPLIT_OUT")) b.split_out = atoi(env) != 0 && gcn && i == n - 1 && (b.path == 2 || b.path == 3);
     if (b.split_out) b.out_fmt = FMT_CL;
     if (b.Wp / b.NC > 16) { rc = fail(nullptr, NASR_ERR_INVALID, "channel count too large for the generic kernel"); break; }
 

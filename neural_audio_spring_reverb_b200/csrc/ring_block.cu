@@ -752,7 +752,8 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             // out_net 1x1 (+ tanh), gcn.py:145-146.  One channel group (16 channels): row-local.  Two groups (32 channels):
             // each CTA has half of the dot product; the halves meet in a word per output sample that the engine pre-fills
             // with an all-ones pattern: atomicExch leaves this group's half there, and whoever gets the OTHER group's half
-            // back (instead of the pattern) adds the two - a + b is the same in either order - and writes the sample
+            // back (instead of the pattern) adds the two - a + b is the same in either order - and writes the sample.
+            // Four groups (64 channels): the same in two levels, three words per sample
             const long long t = t0 + off;
             const bool valid = ok && t < a.T;
             for (int oc = 0; oc < a.out_ch; ++oc) {
@@ -762,10 +763,16 @@ ring_block_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
               for (int c = 0; c < 16; ++c) y = fmaf(o[c], __ldg(wv + c), y);
               if (!valid) continue;
               const long long idx = ((long long)s.b * a.out_ch + oc) * a.T + t;
-              if (n_grp == 2) {
-                const uint32_t other = atomicExch(a.xch + idx, __float_as_uint(y));
+              if (n_grp >= 2) {        // groups (0, 1) and (2, 3) meet in words 0 and 1 of the sample ...
+                const int xw = n_grp == 4 ? 3 : 1;
+                uint32_t other = atomicExch(a.xch + idx * xw + (grp >> 1), __float_as_uint(y));
                 if (other == 0xFFFFFFFFu) continue;
                 y += __uint_as_float(other);
+                if (n_grp == 4) {      // ... and the two pair sums in word 2: (p0 + p1) + (p2 + p3) whoever comes last
+                  other = atomicExch(a.xch + idx * xw + 2, __float_as_uint(y));
+                  if (other == 0xFFFFFFFFu) continue;
+                  y += __uint_as_float(other);
+                }
               }
               if (a.final_tanh) y = tanhf(y);
               ((float*)a.out)[(long long)s.b * a.out_clip_stride + (long long)oc * a.out_rows + a.out_row0 + t] = y;
@@ -1007,7 +1014,7 @@ cudaError_t launch_ring_block(const RingLaunch& L, cudaStream_t s) {
   if (!L.acc && (a.pin || a.raw_out)) return cudaErrorInvalidValue;
   if (L.arch == 1 && a.out_fmt == FMT_FINAL) {   // fused out_net: one group, or two groups meeting in a.xch
     const int g = ring_groups(L.arch, L.cin);
-    if (g > 2 || (g == 2 && !a.xch)) return cudaErrorInvalidValue;
+    if (g > 4 || (g >= 2 && !a.xch)) return cudaErrorInvalidValue;
   }
   {
     static int dbg = -1;

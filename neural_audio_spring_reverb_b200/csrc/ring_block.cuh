@@ -39,7 +39,7 @@ struct RingArgs {
   float slope, inv_sw, inv_sr;
   const float* wout;       // [out_ch][32]
   int out_ch, final_tanh;
-  unsigned int* xch;       // GCN with two channel groups and a fused out_net: one word per output sample [B][out_ch][T], all ones
+  unsigned int* xch;       // GCN with 2 / 4 channel groups and a fused out_net: 1 / 3 words per output sample [B][out_ch][T], all ones
   unsigned int* sat_flag;
   int tma_out;             // rows leave through TMA stores of the staging tiles where the geometry allows
   // tap passes (k > 15, engine.cu): a block's taps are split over several launches of this kernel that hand the conv
