@@ -527,6 +527,46 @@ def test_batch_slicing_under_small_workspace(monkeypatch):
     m.release_engine()
 
 
+def test_tap_pass_block_in_uneven_batch_slices(monkeypatch):
+    """A k = 40 block (tap passes) with the batch cut into slices of 2 + 2 + 1 clips: every slice size has its own span
+    plan, hence its own layout (and size) of the partial plane the passes hand on."""
+    monkeypatch.setenv("NASR_WORKSPACE_MB", "11")
+    cfg = dict(arch="TCN", n_blocks=3, n_channels=32, kernel_size=40, dilation_growth=3, cond_dim=2)
+    sd = O.build_state("TCN", 3, 32, 40, 2, seed=9)
+    m = build_model(cfg, sd, DEV)
+    m.release_engine()
+    x = O.make_input(5, 1, 20000)
+    cond = torch.rand(5, 2)
+    y = m(x.to(DEV), cond.to(DEV))        # 2 planes x 2.56 MB per clip -> slices of 2 clips
+    ref = O.forward(sd, [1, 3, 9], x, cond)
+    assert rel_err(y, ref) <= REL_TOL
+    m.release_engine()
+
+
+@pytest.mark.parametrize("C", [16, 32, 64])
+def test_gcn_fused_out_net_does_not_depend_on_arrival_order(C):
+    """The channel groups of the last GCN ring block exchange their halves of the out_net dot product through a word per
+    sample (whoever comes second adds): a + b is the same either way, so repeated forwards are bit-identical, and they
+    agree with the separate out_net kernel (NASR_SPLIT_OUT=1) to fp32 rounding."""
+    import os
+    cfg = dict(arch="GCN", n_blocks=3, n_channels=C, kernel_size=3, dilation_growth=4, cond_dim=2)
+    sd = O.build_state("GCN", 3, C, 3, 2, seed=70 + C)
+    x = O.make_input(2, 1, 60000).to(DEV)
+    cond = torch.tensor([[0.2, 0.9], [0.7, 0.1]], device=DEV)
+    m = build_model(cfg, sd, DEV)
+    y0 = m(x, cond)
+    for _ in range(5):
+        assert torch.equal(m(x, cond), y0)
+    os.environ["NASR_SPLIT_OUT"] = "1"
+    try:
+        m2 = build_model(cfg, sd, DEV)
+        y2 = m2(x, cond)
+    finally:
+        del os.environ["NASR_SPLIT_OUT"]
+    assert rel_err(y0, y2) <= 2e-6
+    assert rel_err(y0, O.forward(sd, [1, 4, 16], x.cpu(), cond.cpu())) <= REL_TOL
+
+
 def test_ir_deconvolution_matches_direct_convolution():
     """tools/ir_model.py:128-146: the reference's scipy direct convolution (float64) against the cuFFT float64 path."""
     from oracle import post_oracle as P
